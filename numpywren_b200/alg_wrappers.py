@@ -1,0 +1,77 @@
+"""Allocate outputs/intermediates, bind a LambdaPACK program, wrap it in a LambdaPackProgram.
+
+Same call forms and return values as reference numpywren/alg_wrappers.py: ``cholesky`` :16-27,
+``tsqr`` :30-47, ``gemm`` :49-65 → ``(program, {"outputs": [...], "intermediates": [...],
+"compile_time": seconds})``.
+"""
+import time
+
+import numpy as np
+
+from . import config as npw_config
+from . import lambdapack as lp
+from .algs import CHOLESKY, GEMM, TSQR
+from .compiler import lpcompile_for_execution
+from .matrix import BigMatrix
+from .matrix_utils import constant_zeros
+
+
+def cholesky(X, truncate=0):
+    """Tiled Cholesky of the SPD BigMatrix ``X`` → lower factor ``O`` (unwritten upper tiles read as zeros)."""
+    b = X.shard_sizes[0]
+    nb = X.num_blocks(1)
+    S = BigMatrix("Cholesky.Intermediate({0})".format(X.key), shape=(nb + 1, X.shape[0], X.shape[0]),
+                  shard_sizes=(1, b, b), bucket=X.bucket, write_header=True, parent_fn=constant_zeros, device=X.device)
+    O = BigMatrix("Cholesky({0})".format(X.key), shape=(X.shape[0], X.shape[0]), shard_sizes=(b, b), bucket=X.bucket,
+                  write_header=True, parent_fn=constant_zeros, device=X.device)
+    t = time.time()
+    p0 = lpcompile_for_execution(CHOLESKY, inputs=["I"], outputs=["O"])
+    p1 = p0(O, X, S, int(np.ceil(X.shape[0] / b)), truncate)
+    c_time = time.time() - t
+    program = lp.LambdaPackProgram(p1, config=npw_config.default())
+    return program, {"outputs": [O], "intermediates": [S], "compile_time": c_time}
+
+
+def tsqr(X, truncate=0):
+    """Tall-skinny QR of ``X`` (one block column): returns R/V/T trees; final R is R.get_block(levels, 0)."""
+    b_fac = 2
+    assert (X.shard_sizes[1] == X.shape[1])
+    shard_size = X.shard_sizes[0]
+    shard_sizes = X.shard_sizes
+    num_tree_levels = max(int(np.ceil(np.log2(X.num_blocks(0)) / np.log2(b_fac))), 1)
+    R_sharded = BigMatrix("tsqr_R({0})".format(X.key), shape=(num_tree_levels * shard_size, X.shape[0]),
+                          shard_sizes=shard_sizes, bucket=X.bucket, write_header=True, safe=False, device=X.device)
+    T_sharded = BigMatrix("tsqr_T({0})".format(X.key), shape=(num_tree_levels * shard_size * b_fac, X.shape[0]),
+                          shard_sizes=(shard_size * b_fac, shard_size), bucket=X.bucket, write_header=True, safe=False,
+                          device=X.device)
+    V_sharded = BigMatrix("tsqr_V({0})".format(X.key), shape=(num_tree_levels * shard_size * b_fac, X.shape[0]),
+                          shard_sizes=(shard_size * b_fac, shard_size), bucket=X.bucket, write_header=True, safe=False,
+                          device=X.device)
+    t = time.time()
+    p0 = lpcompile_for_execution(TSQR, inputs=["A"], outputs=["Rs"])
+    p1 = p0(X, V_sharded, T_sharded, R_sharded, X.num_blocks(0))
+    c_time = time.time() - t
+    program = lp.LambdaPackProgram(p1, config=npw_config.default())
+    return program, {"outputs": [R_sharded, V_sharded, T_sharded], "intermediates": [], "compile_time": c_time}
+
+
+def gemm(A, B):
+    """Tiled A @ B as M*N*K tile products plus a 4-ary add tree (the DSL GEMM program)."""
+    b_fac = 4
+    assert (A.shape[1] == B.shape[0])
+    assert (A.shard_sizes[1] == B.shard_sizes[0])
+    shard_sizes = (A.shard_sizes[0], B.shard_sizes[1])
+    num_tree_levels = max(int(np.ceil(np.log2(A.num_blocks(1)) / np.log2(b_fac))), 1)
+    Temp = BigMatrix("matmul_test_Temp({0},{1})".format(A.key, B.key),
+                     shape=(A.shape[0], B.shape[1], B.shape[0], num_tree_levels),
+                     shard_sizes=[A.shard_sizes[0], B.shard_sizes[1], 1, 1], bucket=A.bucket, write_header=True,
+                     safe=False, parent_fn=constant_zeros, device=A.device)
+    C_sharded = BigMatrix("matmul_test_C({0},{1})".format(A.key, B.key), shape=(A.shape[0], B.shape[1]),
+                          shard_sizes=shard_sizes, bucket=A.bucket, write_header=True, device=A.device)
+    t = time.time()
+    p0 = lpcompile_for_execution(GEMM, inputs=["A", "B"], outputs=["Out"])
+    # (M, N, K) as the reference passes them (alg_wrappers.py:61)
+    p1 = p0(A, B, A.num_blocks(0), A.num_blocks(1), B.num_blocks(1), Temp, C_sharded)
+    c_time = time.time() - t
+    program = lp.LambdaPackProgram(p1, config=npw_config.default())
+    return program, {"outputs": [C_sharded], "intermediates": [Temp], "compile_time": c_time}

@@ -1,0 +1,398 @@
+"""The LambdaPACK task loop on a B200: ``lambdapack_run(program, ...)``.
+
+Replaces reference numpywren/job_runner.py (worker loop :316-370, read/compute/write pipeline
+:224-309, ``LambdaPackExecutor.run`` :66-159).  The reference worker pulls one ready node from SQS,
+GETs its tiles from S3, runs one NumPy kernel, PUTs the result, then bumps Redis edge counters.
+Here one host thread walks the same ready queue and turns every node into asynchronous GPU work:
+
+  * tiles are torch tensors in HBM taken *by reference* from the BigMatrix store (no copy, no
+    serialisation); results are adopted by reference;
+  * each node's kernel is enqueued on one of a pool of CUDA streams (high-priority streams for the
+    critical-path ops chol / trsm / qr_factor — the reference's ``num_priorities`` idea,
+    lambdapack.py:482) and cross-stream tile dependencies are CUDA events, so the host never waits
+    for the GPU until the ready queue is empty;
+  * SSA intermediates whose only reader is the node that replaces them (``S[i,j,k] → S[i+1,j,k]``,
+    ``S[i,j,i] → O[j,i]``) are updated in place: the SSA version axis of ``S`` aliases one buffer
+    (SURVEY §7 "SSA storage blow-up"); the single-reader property is read off the expanded DAG;
+  * ``chol`` hands the inverted diagonal blocks of its factor to the ``trsm`` nodes that read it.
+
+Program state (node status, edge sums, terminator count, counters) still goes through
+``LambdaPackProgram.post_op`` so the reference's bookkeeping semantics are preserved.
+"""
+from __future__ import annotations
+
+import os
+import time
+import traceback
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import kernels
+from . import lambdapack as lp
+from .compiler import ExpandedNode, _tile_key
+
+HIGH_PRIORITY_KERNELS = ("chol", "trsm", "qr_factor", "qr_factor_triangular")
+
+
+class LRUCache(object):
+    """Tile cache with least-recently-used eviction (reference job_runner.py:34-64).  Kept for the
+    instruction-level API (RemoteRead.cache); the engine itself reads tiles in place from HBM."""
+
+    def __init__(self, max_items=10):
+        self.cache = {}
+        self.key_order = []
+        self.max_items = max_items
+
+    def __setitem__(self, key, value):
+        self.cache[key] = value
+        self._mark(key)
+
+    def __getitem__(self, key):
+        value = self.cache[key]
+        self._mark(key)
+        return value
+
+    def __contains__(self, obj):
+        return obj in self.cache
+
+    def _mark(self, key):
+        if key in self.key_order:
+            self.key_order.remove(key)
+        self.key_order.insert(0, key)
+        while len(self.key_order) > self.max_items:
+            old = self.key_order.pop()
+            del self.cache[old]
+
+
+def calculate_busy_time(rtimes):
+    """Union of [start, end] intervals (reference job_runner.py:162-175)."""
+    events = sorted([(s, 1) for s, _ in rtimes] + [(e, -1) for _, e in rtimes])
+    running, out, start = 0, [], 0
+    for t, d in events:
+        if running == 0 and d == 1:
+            start = t
+        if running == 1 and d == -1:
+            out.append([start, t])
+        running += d
+    return out
+
+
+class StreamPool:
+    """Per-device CUDA streams the engine issues onto."""
+
+    _pools: Dict[int, "StreamPool"] = {}
+
+    def __init__(self, device: torch.device, n_normal: int, n_high: int):
+        self.device = device
+        with torch.cuda.device(device):
+            self.normal = [torch.cuda.Stream(device=device, priority=0) for _ in range(n_normal)]
+            self.high = [torch.cuda.Stream(device=device, priority=-1) for _ in range(n_high)]
+
+    @classmethod
+    def get(cls, device: torch.device, n_normal: int, n_high: int) -> "StreamPool":
+        key = (device.index if device.index is not None else torch.cuda.current_device(), n_normal, n_high)
+        if key not in cls._pools:
+            cls._pools[key] = StreamPool(device, n_normal, n_high)
+        return cls._pools[key]
+
+
+class TileEngine:
+    """Executes ready nodes of one LambdaPackProgram on one GPU (one process = one GPU)."""
+
+    def __init__(self, program: lp.LambdaPackProgram, streams: int = 4, high_streams: int = 2, inplace: bool = True,
+                 consume_inputs: bool = False, profile: bool = False, comm=None):
+        self.program = program
+        self.compiled = program.program
+        self.inplace = inplace
+        self.consume_inputs = consume_inputs
+        self.profile = profile
+        self.comm = comm
+        self.device = None
+        self.pool: Optional[StreamPool] = None
+        self.n_streams, self.n_high = streams, high_streams
+        self.tile_event: Dict[Any, Tuple[torch.cuda.Event, torch.cuda.Stream]] = {}
+        self.invdiag: Dict[Any, torch.Tensor] = {}
+        self.infos: List[Tuple[ExpandedNode, torch.Tensor]] = []
+        self.timeline: List[Tuple[ExpandedNode, torch.cuda.Event, torch.cuda.Event, int]] = []
+        self.launched = 0
+        self.input_names = set(self.compiled.inputs)
+        self._input_mats = {id(self.compiled.scope[n]) for n in self.input_names if n in self.compiled.scope}
+        self._prio: Optional[List[int]] = None
+
+    # ------------------------------------------------------------------ priorities
+    def priorities(self) -> List[int]:
+        """Longest path to a sink (unit costs): the critical-path priority used to order the ready queue."""
+        if self._prio is None:
+            nodes = self.compiled.nodes
+            prio = [0] * len(nodes)
+            indeg = [len(n.children) for n in nodes]
+            stack = [n.nid for n in nodes if not n.children]
+            while stack:
+                v = stack.pop()
+                for p in nodes[v].parents:
+                    if prio[v] + 1 > prio[p]:
+                        prio[p] = prio[v] + 1
+                    indeg[p] -= 1
+                    if indeg[p] == 0:
+                        stack.append(p)
+            self._prio = prio
+        return self._prio
+
+    # ------------------------------------------------------------------ plumbing
+    def _ensure_device(self, tensor_device: torch.device):
+        if self.pool is None:
+            if tensor_device.type != "cuda":
+                raise kernels._capi.NpwError(
+                    f"lambdapack_run: tiles live on {tensor_device}; the B200 engine has no CPU execution path")
+            self.device = tensor_device
+            self.pool = StreamPool.get(tensor_device, self.n_streams, self.n_high)
+            # everything already in the store was produced on whatever stream the caller used
+            self._entry_event = torch.cuda.Event()
+            self._entry_event.record(torch.cuda.current_stream(tensor_device))
+            self._entered = set()
+
+    def _stream_for(self, node: ExpandedNode) -> torch.cuda.Stream:
+        m, idx = node.writes[0]
+        true_idx = m.true_block_idx(*idx)
+        tail = true_idx[-2:] if len(true_idx) == 3 else true_idx
+        h = 0
+        for v in tail:
+            h = h * 1000003 + int(v) + 7
+        pool = self.pool.high if (node.call.compute_name in HIGH_PRIORITY_KERNELS and self.pool.high) else self.pool.normal
+        return pool[h % len(pool)]
+
+    def _wait_tile(self, key, stream):
+        ev = self.tile_event.get(key)
+        if ev is not None and ev[1] is not stream:
+            stream.wait_event(ev[0])
+
+    def _owned_input(self, m, idx, ref) -> bool:
+        """May the node overwrite this stored tile?  Only if it is the tile's single reader and the tile is an
+        intermediate (or inputs were declared consumable)."""
+        if not self.inplace or ref is None:
+            return False
+        if id(m) in self._input_mats and not self.consume_inputs:
+            return False
+        if getattr(m, "transposed", False):
+            return False
+        return self.compiled.num_readers(m, idx) == 1
+
+    def _read(self, m, idx, stream):
+        """→ (2-D/N-D tile tensor, stored_ref_or_None, tile_key).  Never copies unless lambdav/transposed views force it."""
+        key = _tile_key(m, idx)
+        self._wait_tile(key, stream)
+        ref = m._get_block_ref(*idx) if hasattr(m, "_get_block_ref") else None
+        shifted = (len(set(idx)) == 1 and len(set(m.shape)) == 1 and len(m.shape) != 1 and m.lambdav != 0)
+        if ref is None or shifted:
+            # default tile (parent_fn), transposed view, or diagonal shift: the public path makes a private copy
+            tile = m.get_block(*idx)
+            return tile, None, key, True
+        tile = ref.squeeze() if m.autosqueeze else ref
+        return tile, ref, key, False
+
+    def _store(self, m, idx, tile, stream, event):
+        shape = m.block_shape(*idx) if hasattr(m, "block_shape") else tuple(tile.shape)
+        if tuple(tile.shape) != tuple(shape):
+            if m.autosqueeze and list(tile.shape) == [x for x in shape if x != 1]:
+                tile = tile.reshape(shape)
+            elif m.safe:
+                raise Exception("{2} Incompatible block size: {0} vs {1}".format(tuple(tile.shape), shape, m))
+        if not tile.is_contiguous():
+            tile = tile.contiguous()
+        m._put_block_ref(tile, *idx)
+        self.tile_event[_tile_key(m, idx)] = (event, stream)
+
+    # ------------------------------------------------------------------ one node
+    def run_node(self, node: ExpandedNode):
+        first_m = node.reads[0][0] if node.reads else node.writes[0][0]
+        self._ensure_device(first_m.device)
+        stream = self._stream_for(node)
+        name = node.call.compute_name
+        fn = node.call.compute
+        with torch.cuda.stream(stream):
+            if id(stream) not in self._entered:
+                self._entered.add(id(stream))
+                stream.wait_event(self._entry_event)
+            t0 = None
+            if self.profile:
+                t0 = torch.cuda.Event(enable_timing=True)
+                t0.record(stream)
+            tiles, refs, keys, private = [], [], [], []
+            for (m, idx) in node.reads:
+                tile, ref, key, priv = self._read(m, idx, stream)
+                tiles.append(tile); refs.append(ref); keys.append(key); private.append(priv)
+            args = []
+            for kind, j in node.arg_layout:
+                if kind == "read":
+                    args.append(tiles[j])
+                elif isinstance(node.scalars[j], float):  # ints are dropped (reference lambdapack.py:364-368)
+                    args.append(node.scalars[j])
+            consumed = None  # index of the read whose buffer becomes the output
+
+            def can_overwrite(j):
+                m, idx = node.reads[j]
+                return tiles[j].dim() == 2 and tiles[j].is_contiguous() and (
+                    private[j] or self._owned_input(m, idx, refs[j]))
+
+            if fn is kernels.syrk and len(args) == 3:
+                out = args[0] if can_overwrite(0) else None
+                consumed = 0 if out is not None else None
+                results = kernels.syrk(args[0], args[1], args[2], out=out)
+            elif fn is kernels.trsm and len(args) == 2:
+                out = args[1] if can_overwrite(1) else None
+                consumed = 1 if out is not None else None
+                results = kernels.trsm_with_inverse(args[0], args[1], self.invdiag.get(keys[0]), out=out)
+            elif fn is kernels.chol and len(args) == 1:
+                out = args[0] if can_overwrite(0) else None
+                consumed = 0 if out is not None else None
+                L, info, inv = kernels.chol_async(args[0], want_inverse=True, out=out)
+                self.infos.append((node, info))
+                self.invdiag[_tile_key(*node.writes[0])] = inv
+                results = L
+            else:
+                results = fn(*args, **(node.call.kwargs or {}))
+            if isinstance(results, tuple):
+                if len(results) != len(node.writes):
+                    raise Exception("Expected {0} results, got {1}".format(len(node.writes), len(results)))
+            else:
+                if len(node.writes) != 1:
+                    raise Exception("Expected {0} results, got {1}".format(len(node.writes), 1))
+                results = (results,)
+            if consumed is not None and not private[consumed]:
+                m, idx = node.reads[consumed]
+                m.delete_block(*idx)  # the buffer now belongs to the output tile
+            ev = torch.cuda.Event()
+            for (m, idx), tile in zip(node.writes, results):
+                self._store(m, idx, tile, stream, ev)
+            ev.record(stream)
+            if self.profile:
+                t1 = torch.cuda.Event(enable_timing=True)
+                t1.record(stream)
+                self.timeline.append((node, t0, t1, id(stream)))
+        self.launched += 1
+        # counters (reference job_runner.py:236-237, 265-266, 293-296)
+        prog = self.program
+        fl = getattr(fn, "flops", None)
+        if fl is not None:
+            try:
+                prog.incr_flops(int(fl(*[a for a in args if isinstance(a, torch.Tensor)])))
+            except Exception:
+                pass
+        for (m, _) in node.reads:
+            prog.incr_read(lp._nbytes(m))
+        for (m, _) in node.writes:
+            prog.incr_write(lp._nbytes(m))
+
+    # ------------------------------------------------------------------ drain
+    def finish(self):
+        """Wait for the device and surface asynchronous kernel failures (LAPACK-style info codes)."""
+        if self.device is not None:
+            torch.cuda.synchronize(self.device)
+        bad = []
+        for node, info in self.infos:
+            code = int(info.item())
+            if code != 0:
+                bad.append((node, code))
+        self.infos = []
+        return bad
+
+
+def _engine_for(program: lp.LambdaPackProgram, **opts) -> TileEngine:
+    eng = getattr(program, "_engine", None)
+    if eng is None:
+        eng = TileEngine(program, **opts)
+        program._engine = eng
+        prio = eng.priorities()
+        compiled = program.program
+        program._priority_fn = lambda e, v: prio[compiled.node(e, v).nid]
+    return eng
+
+
+def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, timeout=200, idle_timeout=5,
+                   msg_vis_timeout_jitter=15, compute_threads=1, streams=None, high_streams=None, inplace=None,
+                   consume_inputs=False, profile=False):
+    """Run ready nodes of ``program`` until it finishes, fails, or ``timeout`` seconds elapse.
+
+    Signature and return keys follow reference job_runner.lambdapack_run (:316-370).  ``pipeline_width``
+    (the reference's read/compute/write overlap depth) sets the number of CUDA streams unless ``streams``
+    is given; ``cache_size``, ``msg_vis_timeout*`` and ``compute_threads`` have no meaning without
+    S3/SQS/BLAS threads and are accepted for compatibility.  Extra keywords tune the B200 engine.
+    """
+    program.incr_up(1)
+    with program._lock:
+        program._runner_active += 1
+    lambda_start = time.time()
+    n_streams = streams if streams is not None else int(os.environ.get("NPW_B200_STREAMS", max(1, min(8, pipeline_width))))
+    n_high = high_streams if high_streams is not None else int(os.environ.get("NPW_B200_HIGH_STREAMS", 2))
+    if inplace is None:
+        inplace = os.environ.get("NPW_B200_INPLACE", "1") != "0"
+    eng = _engine_for(program, streams=n_streams, high_streams=n_high, inplace=inplace, consume_inputs=consume_inputs,
+                      profile=profile)
+    program._defer_success = True
+    executed, refs = [], []
+    try:
+        while program.program_status() == lp.PS.RUNNING:
+            if time.time() - lambda_start > timeout:
+                break
+            item = program._dequeue()
+            if item is None:
+                break
+            expr_idx, var_values = item
+            status = program.get_node_status(expr_idx, var_values)
+            if status == lp.NS.FINISHED:
+                program.incr_repeated_finish()
+                continue
+            if status == lp.NS.NOT_READY:
+                program.incr_not_ready()
+                continue
+            node = program.program.node(expr_idx, var_values)
+            try:
+                if status in (lp.NS.READY, lp.NS.RUNNING):
+                    if status == lp.NS.RUNNING:
+                        program.incr_repeated_compute()
+                    program.set_node_status(expr_idx, var_values, lp.NS.RUNNING)
+                    eng.run_node(node)
+                else:
+                    program.incr_repeated_post_op()
+                program.post_op(expr_idx, var_values, lp.PS.SUCCESS, None)
+                program.set_node_status(expr_idx, var_values, lp.NS.FINISHED)
+            except Exception:
+                tb = traceback.format_exc()
+                program.handle_exception("EXCEPTION", tb=tb, expr_idx=expr_idx, var_values=var_values)
+                raise
+            executed.append((expr_idx, var_values))
+            refs.append((expr_idx, var_values))
+        bad = eng.finish()
+        if bad:
+            node, code = bad[0]
+            program.handle_exception("COMPUTE EXCEPTION", tb="", expr_idx=node.expr_idx, var_values=node.var_values)
+            raise np.linalg.LinAlgError(
+                "Matrix is not positive definite (tile task {0}{1}: leading minor {2})".format(
+                    node.call.compute_name, node.var_values, code))
+        with program._lock:
+            if getattr(program, "_all_terminators_done", False) and program._status == lp.PS.RUNNING:
+                program._status = lp.PS.SUCCESS
+    finally:
+        program.decr_up(1)
+        with program._lock:
+            program._runner_active -= 1
+    lambda_stop = time.time()
+    return {"up_time": [lambda_start, lambda_stop],
+            "exec_time": calculate_busy_time([[lambda_start, lambda_stop]]) if executed else [],
+            "executed_messages": executed,
+            "operator_refs": refs,
+            "log": None}
+
+
+def node_timeline(program):
+    """Per-node GPU times (ms) recorded when ``profile=True``: [(compute_name, var_values, start_ms, end_ms, stream)]."""
+    eng = getattr(program, "_engine", None)
+    if eng is None or not eng.timeline:
+        return []
+    base = eng.timeline[0][1]
+    out = []
+    for node, t0, t1, sid in eng.timeline:
+        out.append((node.call.compute_name, dict(node.var_values), base.elapsed_time(t0), base.elapsed_time(t1), sid))
+    return out

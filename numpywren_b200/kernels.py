@@ -125,12 +125,22 @@ def add_matrices(*args, **kwargs):
     return out
 
 
-def syrk(s, x, y, *args, **kwargs):
-    """s - x.dot(y.T)  — kernels.py:212-215."""
+def _out_tile(out, shape, device, name):
+    """Validate a caller-provided output tile (row-major, right shape) or allocate one."""
+    if out is None:
+        return torch.empty(shape, dtype=torch.float64, device=device)
+    _check_tile(out, name)
+    if tuple(out.shape) != tuple(shape) or out.stride(1) != 1 or out.stride(0) < max(1, shape[1]):
+        raise ValueError(f"{name}: expected a row-major {tuple(shape)} tile, got {tuple(out.shape)} strides {out.stride()}")
+    return out
+
+
+def syrk(s, x, y, *args, out=None, **kwargs):
+    """s - x.dot(y.T)  — kernels.py:212-215.  ``out`` (scheduler use) may be ``s`` itself: in-place update."""
     _check_tile(s, "s")
     _check_tile(x, "x")
     _check_tile(y, "y")
-    out = torch.empty((x.shape[0], y.shape[0]), dtype=torch.float64, device=s.device)
+    out = _out_tile(out, (x.shape[0], y.shape[0]), s.device, "out")
     if tuple(s.shape) != tuple(out.shape):
         raise ValueError(f"operands could not be broadcast together with shapes {tuple(s.shape)} {tuple(out.shape)}")
     sm = _rowmajor(s, "s")
@@ -155,7 +165,7 @@ def _syrk_flops(s, x, y):
 syrk.flops = _syrk_flops
 
 
-def chol_async(x, want_inverse=True):
+def chol_async(x, want_inverse=True, out=None):
     """Enqueue the tile Cholesky; returns (L, info[int32 device scalar], invdiag or None).
 
     No host synchronisation: ``info`` holds LAPACK's INFO once the stream reaches it.
@@ -167,7 +177,7 @@ def chol_async(x, want_inverse=True):
         raise np.linalg.LinAlgError("Last 2 dimensions of the array must be square")
     lib = _capi.load()
     dev = x.device
-    L = torch.empty((n, n), dtype=torch.float64, device=dev)
+    L = _out_tile(out, (n, n), dev, "out")
     info = torch.empty((), dtype=torch.int32, device=dev)
     work = torch.empty(max(1, lib.npw_potrf_work_bytes(n) // 8), dtype=torch.float64, device=dev)
     inv = None
@@ -195,7 +205,7 @@ def _chol_flops(x):
 chol.flops = _chol_flops
 
 
-def trsm_with_inverse(x, y, invdiag=None):
+def trsm_with_inverse(x, y, invdiag=None, out=None):
     """y @ inv(x).T for lower-triangular x, optionally reusing chol_async's inverted diagonal blocks."""
     _check_tile(x, "x")
     y = _rowmajor(y, "y")
@@ -207,7 +217,7 @@ def trsm_with_inverse(x, y, invdiag=None):
         raise ValueError(f"trsm: shapes {tuple(x.shape)} and {tuple(y.shape)} are incompatible")
     xm = _rowmajor(x, "x")
     lib = _capi.load()
-    out = torch.empty((m, n), dtype=torch.float64, device=y.device)
+    out = _out_tile(out, (m, n), y.device, "out")
     work = torch.empty(max(1, lib.npw_trsm_work_bytes(m, n) // 8), dtype=torch.float64, device=y.device)
     rc = lib.npw_trsm_rlt_f64(out.data_ptr(), max(1, out.stride(0)), xm.data_ptr(), max(1, xm.stride(0)), y.data_ptr(),
                               max(1, y.stride(0)), m, n, invdiag.data_ptr() if invdiag is not None else 0, work.data_ptr(),

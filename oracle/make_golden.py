@@ -1,0 +1,319 @@
+"""Generate tests/golden/* by running the UNMODIFIED reference (/root/reference/numpywren).
+
+Run here (the build container) only:  python oracle/make_golden.py
+The GPU box has no /root/reference; tests read the committed fixtures instead.
+
+What runs is the reference's own code: algs.py DSL sources → frontend.LambdaPackParse /
+TypeCheck / BackendGenerate → compiler.{find_starters,find_children,find_parents,eval_remote_call}
+→ lambdapack.Remote{Read,Call,Write} → kernels.{chol,trsm,syrk,gemm,add_matrices}.
+Shims: stub modules for boto3/botocore/aiobotocore/redis/pywren (not
+installed, no network); np.product = np.prod for numpy >= 2; an in-memory dict behind
+BigMatrix.get_block_async / put_block_async that keeps the reference's parent_fn / autosqueeze /
+lambdav logic (matrix.py:294-309) and put-side reshape/safe logic (matrix.py:349-358).
+For TSQR only, kernels.fast_qr is replaced by a scipy.linalg.lapack.dgeqrt restatement because
+its f2py module (dgeqrt3) exists only in the authors' S3 bucket (kernels.py:22-40,86-89).
+"""
+import asyncio
+import json
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def install_stubs():
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    for name in ["boto3", "botocore", "botocore.exceptions", "aiobotocore", "redis", "redis.exceptions", "pywren",
+                 "pywren.wrenconfig", "pywren.serialize", "pywren.executor", "pywren.future", "pywren.storage",
+                 "pywren.ec2standalone", "pywren.queues", "tblib", "watchtower", "aiohttp", "aiohttp.client_exceptions"]:
+        if name not in sys.modules or name.startswith(("boto", "aiobot", "redis", "pywren", "tblib", "watchtower")):
+            try:
+                if name.startswith("aiohttp"):
+                    __import__(name)
+                    continue
+            except Exception:
+                pass
+            mod(name)
+    sys.modules["pywren.wrenconfig"].default = lambda: {"s3": {"bucket": "b"}, "account": {"aws_region": "r"}}
+    sys.modules["pywren.serialize"].serialize = object
+    sys.modules["pywren.executor"].Executor = object
+    sys.modules["pywren"].wrenconfig = sys.modules["pywren.wrenconfig"]
+    sys.modules["pywren"].serialize = sys.modules["pywren.serialize"]
+    sys.modules["pywren"].executor = sys.modules["pywren.executor"]
+    sys.modules["botocore"].exceptions = sys.modules["botocore.exceptions"]
+    sys.modules["botocore.exceptions"].ClientError = type("ClientError", (Exception,), {})
+    sys.modules["redis"].exceptions = sys.modules["redis.exceptions"]
+    sys.modules["redis.exceptions"].WatchError = type("WatchError", (Exception,), {})
+    sys.modules["redis"].StrictRedis = object
+    if not hasattr(np, "product"):
+        np.product = np.prod
+    if not hasattr(np, "int"):
+        np.int = int
+
+
+def import_reference():
+    install_stubs()
+    sys.path.insert(0, REF)
+    import dill  # noqa: F401
+    import numpywren  # noqa: F401
+    from numpywren import algs, compiler, frontend, kernels, lambdapack, matrix, matrix_utils
+    STORE = {}
+
+    async def get_block_async(self, loop, *block_idx):
+        # matrix.py:273-310 with the S3 HEAD/GET replaced by a dict lookup
+        if len(block_idx) != len(self.shape):
+            raise Exception("Get block query does not match shape")
+        key = (self.key, tuple(int(x) for x in block_idx))
+        import dill as _d
+        pf = _d.loads(self.parent_fn)
+        if key not in STORE and pf is None:
+            raise Exception("Key does {0} not exist, and no parent function prescripted".format(key))
+        elif key not in STORE:
+            X_block = await pf(self, loop, *block_idx)
+        else:
+            X_block = STORE[key].copy()
+        if self.autosqueeze:
+            X_block = np.squeeze(X_block)
+        if len(set(block_idx)) == 1 and len(set(self.shape)) == 1 and len(self.shape) != 1:
+            idxs = np.diag_indices(X_block.shape[0])
+            X_block[idxs] += self.lambdav
+        return X_block
+
+    async def put_block_async(self, block, loop=None, *block_idx, no_overwrite=False):
+        # matrix.py:318-361 with the S3 PUT replaced by a dict store
+        real_idxs = self.__block_idx_to_real_idx__(block_idx)
+        current_shape = tuple([e - s for s, e in real_idxs])
+        if self.autosqueeze:
+            if list(block.shape) == [x for x in current_shape if x != 1]:
+                block = block.reshape(current_shape)
+        if self.safe and block.shape != current_shape:
+            raise Exception("Incompatible block size: {0} vs {1}".format(block.shape, current_shape))
+        STORE[(self.key, tuple(int(x) for x in block_idx))] = np.array(block, copy=True)
+        return None
+
+    matrix.BigMatrix.get_block_async = get_block_async
+    matrix.BigMatrix.put_block_async = put_block_async
+    return dict(algs=algs, compiler=compiler, frontend=frontend, kernels=kernels, lp=lambdapack, matrix=matrix,
+                matrix_utils=matrix_utils, STORE=STORE)
+
+
+def node_key(node):
+    return (int(node[0]), tuple(sorted((str(k), int(v)) for k, v in node[1].items())))
+
+
+def replay(ref, prog, record_dag=False):
+    """Kahn replay driven by the reference's own starters/find_children/find_parents/eval_expr
+    (mirrors lambdapack.py:545-592).  Returns (#nodes executed, dag dict or None)."""
+    loop = asyncio.new_event_loop()
+    asyncio.set_event_loop(loop)
+    ready = [(int(e), dict(v)) for e, v in prog.starters]
+    indeg = {}
+    done = set()
+    order = []
+    dag = {}
+    while ready:
+        e, v = ready.pop(0)
+        k = node_key((e, v))
+        if k in done:
+            continue
+        ib = prog.eval_expr(e, v)
+        for ins in ib.instrs:
+            loop.run_until_complete(ins())
+        done.add(k)
+        order.append(k)
+        children = prog.find_children(e, v)
+        if record_dag:
+            dag[repr(k)] = {"children": sorted(repr(node_key(c)) for c in children),
+                            "parents": sorted(repr(node_key(p)) for p in prog.find_parents(e, v))}
+        for c in children:
+            ck = node_key(c)
+            indeg[ck] = indeg.get(ck, 0) + 1
+            if indeg[ck] == len(prog.find_parents(c[0], c[1])):
+                ready.append((int(c[0]), {str(a): int(b) for a, b in c[1].items()}))
+    loop.close()
+    return len(order), (dag if record_dag else None)
+
+
+def golden_cholesky(ref, n, b, seed, name, lambdav=0.0, record_dag=False):
+    BigMatrix = ref["matrix"].BigMatrix
+    cz = ref["matrix_utils"].constant_zeros
+    ref["STORE"].clear()
+    rs = np.random.RandomState(seed)
+    X = rs.randn(n, n)
+    A = X.dot(X.T) + np.eye(n)  # tests/test_alg_correctness.py:32-33
+    I = BigMatrix(f"A_{name}", shape=(n, n), shard_sizes=(b, b), write_header=False, lambdav=lambdav)
+    for bi in I._block_idxs():
+        sl = tuple(slice(s, e) for s, e in I.__block_idx_to_real_idx__(bi))
+        ref["STORE"][(I.key, bi)] = A[sl].copy()
+    nb = int(np.ceil(n / b))
+    S = BigMatrix(f"S_{name}", shape=(nb + 1, n, n), shard_sizes=(1, b, b), write_header=False, parent_fn=cz)
+    O = BigMatrix(f"O_{name}", shape=(n, n), shard_sizes=(b, b), write_header=False, parent_fn=cz)
+    p0 = ref["compiler"].lpcompile_for_execution(ref["algs"].CHOLESKY, inputs=["I"], outputs=["O"])
+    prog = p0(O, I, S, nb, 0)
+    nnodes, dag = replay(ref, prog, record_dag)
+    L = np.zeros((n, n))
+    for bi in O._block_idxs():
+        sl = tuple(slice(s, e) for s, e in O.__block_idx_to_real_idx__(bi))
+        if (O.key, bi) in ref["STORE"]:
+            L[sl] = ref["STORE"][(O.key, bi)]
+    s_tiles = {f"S_{k[1][0]}_{k[1][1]}_{k[1][2]}": v for k, v in ref["STORE"].items() if k[0] == S.key}
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), A=A, L=L, n=n, b=b, lambdav=lambdav, nnodes=nnodes, **s_tiles)
+    print(name, "nodes", nnodes, "starters", prog.starters, "terminators", prog.num_terminators,
+          "|L - np.linalg.cholesky|max", np.abs(L - np.linalg.cholesky(A + lambdav * np.eye(n))).max())
+    return {"nnodes": nnodes, "num_terminators": int(prog.num_terminators), "starters": [repr(node_key(s)) for s in prog.starters],
+            "dag": dag}
+
+
+def golden_gemm(ref, n, b, seed, name, record_dag=False):
+    BigMatrix = ref["matrix"].BigMatrix
+    cz = ref["matrix_utils"].constant_zeros
+    ref["STORE"].clear()
+    rs = np.random.RandomState(seed)
+    A = rs.randn(n, n)
+    B = rs.randn(n, n)
+    Am = BigMatrix(f"A_{name}", shape=(n, n), shard_sizes=(b, b), write_header=False)
+    Bm = BigMatrix(f"B_{name}", shape=(n, n), shard_sizes=(b, b), write_header=False)
+    for M_, X_ in ((Am, A), (Bm, B)):
+        for bi in M_._block_idxs():
+            sl = tuple(slice(s, e) for s, e in M_.__block_idx_to_real_idx__(bi))
+            ref["STORE"][(M_.key, bi)] = X_[sl].copy()
+    b_fac = 4
+    num_tree_levels = max(int(np.ceil(np.log2(Am.num_blocks(1)) / np.log2(b_fac))), 1)  # alg_wrappers.py:54
+    Temp = BigMatrix(f"T_{name}", shape=(n, n, n, num_tree_levels), shard_sizes=[b, b, 1, 1], write_header=False, safe=False,
+                     parent_fn=cz)
+    C = BigMatrix(f"C_{name}", shape=(n, n), shard_sizes=(b, b), write_header=False)
+    p0 = ref["compiler"].lpcompile_for_execution(ref["algs"].GEMM, inputs=["A", "B"], outputs=["Out"])
+    prog = p0(Am, Bm, Am.num_blocks(0), Am.num_blocks(1), Bm.num_blocks(1), Temp, C)
+    nnodes, dag = replay(ref, prog, record_dag)
+    Cout = np.zeros((n, n))
+    for bi in C._block_idxs():
+        sl = tuple(slice(s, e) for s, e in C.__block_idx_to_real_idx__(bi))
+        Cout[sl] = ref["STORE"][(C.key, bi)]
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), A=A, B=B, C=Cout, n=n, b=b, nnodes=nnodes)
+    print(name, "nodes", nnodes, "starters", len(prog.starters), "terminators", prog.num_terminators, "|C - A@B|max",
+          np.abs(Cout - A.dot(B)).max())
+    return {"nnodes": nnodes, "num_terminators": int(prog.num_terminators), "num_starters": len(prog.starters), "dag": dag}
+
+
+def golden_tsqr(ref, m, b, seed, name, record_dag=False):
+    """test_tsqr recipe (tests/test_alg_correctness.py:72-102) with the scipy dgeqrt stand-in for fast_qr."""
+    import scipy.linalg
+    kernels = ref["kernels"]
+
+    def fast_qr_scipy(x):  # kernels.py:86-105 with lapack.dgeqrt(nb=n) == dgeqrt3's single T
+        mm, nn = x.shape
+        k = min(mm, nn)
+        a, t, info = scipy.linalg.lapack.dgeqrt(nn, np.asfortranarray(x))
+        r = np.triu(a)
+        v = np.triu(a.T).T.copy()
+        v = v[:, :k]
+        v[np.diag_indices(min(v.shape[0], v.shape[1]))] = 1
+        r = r[:r.shape[1], :]
+        return v, np.triu(t), r
+
+    kernels.fast_qr = fast_qr_scipy
+    BigMatrix = ref["matrix"].BigMatrix
+    ref["STORE"].clear()
+    np.random.seed(seed)
+    X = np.random.randn(m, b)
+    Xm = BigMatrix(f"X_{name}", shape=X.shape, shard_sizes=(b, b), write_header=False)
+    for bi in Xm._block_idxs():
+        sl = tuple(slice(s, e) for s, e in Xm.__block_idx_to_real_idx__(bi))
+        ref["STORE"][(Xm.key, bi)] = X[sl].copy()
+    b_fac = 2
+    nlev = max(int(np.ceil(np.log2(Xm.num_blocks(0)) / np.log2(b_fac))), 1)  # alg_wrappers.py:35
+    R = BigMatrix(f"R_{name}", shape=(nlev * b, m), shard_sizes=(b, b), write_header=False, safe=False)
+    T = BigMatrix(f"Tq_{name}", shape=(nlev * b * b_fac, m), shard_sizes=(b * b_fac, b), write_header=False, safe=False)
+    V = BigMatrix(f"V_{name}", shape=(nlev * b * b_fac, m), shard_sizes=(b * b_fac, b), write_header=False, safe=False)
+    p0 = ref["compiler"].lpcompile_for_execution(ref["algs"].TSQR, inputs=["A"], outputs=["Rs"])
+    prog = p0(Xm, V, T, R, Xm.num_blocks(0))
+    nnodes, dag = replay(ref, prog, record_dag)
+    out = {f"{k[0].split('_')[0]}_{k[1][0]}_{k[1][1]}": v for k, v in ref["STORE"].items() if k[0] in (R.key, T.key, V.key)}
+    Rfin = ref["STORE"][(R.key, (nlev, 0))]
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), X=X, R=Rfin, m=m, b=b, nlev=nlev, nnodes=nnodes, **out)
+    Rnp = np.linalg.qr(X)[1]
+    print(name, "nodes", nnodes, "starters", len(prog.starters), "terminators", prog.num_terminators, "| |R| - |R_np| |max",
+          np.abs(np.abs(Rfin) - np.abs(Rnp)).max())
+    return {"nnodes": nnodes, "num_terminators": int(prog.num_terminators), "num_starters": len(prog.starters), "dag": dag}
+
+
+def golden_kernels(ref):
+    """Per-kernel vectors straight from reference kernels.py on seeded tiles."""
+    k = ref["kernels"]
+    rs = np.random.RandomState(7)
+    b = 48
+    s = rs.randn(b, b); x = rs.randn(b, 40); y = rs.randn(b, 40)
+    a = rs.randn(b, b); spd = a.dot(a.T) + b * np.eye(b)
+    L = k.chol(spd)
+    bmat = rs.randn(b, b)
+    parts = [rs.randn(b, b) for _ in range(4)]
+    ga = rs.randn(40, 56); gb = rs.randn(56, 24)
+    np.savez_compressed(os.path.join(OUT, "kernels.npz"), s=s, x=x, y=y, syrk=k.syrk(s, x, y), spd=spd, chol=L, trsm_b=bmat,
+                        trsm=np.ascontiguousarray(k.trsm(L, bmat)), p0=parts[0], p1=parts[1], p2=parts[2], p3=parts[3],
+                        add=k.add_matrices(*parts), ga=ga, gb=gb, gemm=k.gemm(ga, gb), mul=k.mul(parts[0], parts[1]))
+    print("kernels.npz written")
+
+
+def structure_counts(ref):
+    """Known answers of tests/test_starters_terminators.py:14-43 re-derived from the reference itself, plus
+    node counts from walk_program for a range of sizes."""
+    comp, algs = ref["compiler"], ref["algs"]
+    BigMatrix = ref["matrix"].BigMatrix
+
+    def dummy(nd):
+        return BigMatrix("dummy%d" % nd, shape=tuple([1000] * nd), shard_sizes=tuple([1] * nd), write_header=False)
+
+    out = {}
+    for nb in (1, 2, 3, 4, 6, 8, 16):
+        prog = comp.lpcompile(algs.CHOLESKY)(dummy(2), dummy(2), dummy(3), nb, 0)
+        states = comp.walk_program(prog)
+        per = {}
+        for e, _ in states:
+            per[int(e)] = per.get(int(e), 0) + 1
+        out[f"cholesky_{nb}"] = {"nodes": len(states), "per_expr": per,
+                                 "starters": [repr(node_key(s)) for s in comp.find_starters(prog, ["I"])],
+                                 "terminators": len(comp.find_terminators(prog, ["O"]))}
+    prog = comp.lpcompile(algs.CHOLESKY)(dummy(2), dummy(2), dummy(3), 313, 0)
+    out["cholesky_313"] = {"starters": [repr(node_key(s)) for s in comp.find_starters(prog, ["I"])],
+                           "terminators": len(comp.find_terminators(prog, ["O"]))}
+    for (M, N, K) in ((4, 4, 4), (2, 2, 2), (3, 3, 5), (2, 2, 16)):
+        prog = comp.lpcompile(algs.GEMM)(dummy(2), dummy(2), M, N, K, dummy(4), dummy(3))
+        out[f"gemm_{M}_{N}_{K}"] = {"nodes": len(comp.walk_program(prog)), "starters": len(comp.find_starters(prog, ["A", "B"])),
+                                    "terminators": len(comp.find_terminators(prog, ["Out"]))}
+    for N in (1, 2, 4, 8, 16, 64):
+        prog = comp.lpcompile(algs.TSQR)(dummy(2), dummy(2), dummy(2), dummy(2), N)
+        out[f"tsqr_{N}"] = {"nodes": len(comp.walk_program(prog)), "starters": len(comp.find_starters(prog, ["A"])),
+                            "terminators": len(comp.find_terminators(prog, ["Rs"]))}
+    return out
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ref = import_reference()
+    meta = {}
+    golden_kernels(ref)
+    meta["cholesky_64_8"] = golden_cholesky(ref, 64, 8, 0, "cholesky_64_8")                    # test_cholesky shape
+    meta["cholesky_64_16"] = golden_cholesky(ref, 64, 16, 1, "cholesky_64_16", record_dag=True)  # test_cholesky_lambda shape
+    meta["cholesky_60_16"] = golden_cholesky(ref, 60, 16, 2, "cholesky_60_16")                  # ragged last tile
+    meta["cholesky_64_32_lam"] = golden_cholesky(ref, 64, 32, 3, "cholesky_64_32_lam", lambdav=2.5)  # lambdav on diagonal reads
+    meta["gemm_64_16"] = golden_gemm(ref, 64, 16, 4, "gemm_64_16", record_dag=True)              # test_gemm shape (4x4x4 tiles)
+    meta["gemm_32_16"] = golden_gemm(ref, 32, 16, 5, "gemm_32_16")
+    meta["tsqr_256_32"] = golden_tsqr(ref, 256, 32, 1, "tsqr_256_32", record_dag=True)           # test_tsqr shape
+    meta["tsqr_128_16"] = golden_tsqr(ref, 128, 16, 2, "tsqr_128_16")
+    meta["structure"] = structure_counts(ref)
+    with open(os.path.join(OUT, "structure.json"), "w") as f:
+        json.dump(meta, f, indent=0, sort_keys=True)
+    print("wrote", OUT)
+
+
+if __name__ == "__main__":
+    main()
