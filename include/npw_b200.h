@@ -55,6 +55,16 @@ int npw_syrk_f64(double* C_out, int64_t ldc,
                  const double* Y, int64_t ldy,
                  int64_t m, int64_t n, int64_t k, npw_stream_t stream);
 
+/* Same update restricted to the 128x128 CTA tiles that touch the lower triangle
+ * (row >= col): the scheduler uses it for DIAGONAL tiles S[i,j,j], whose strict
+ * upper triangle is never read again (kernels.chol reads the lower triangle
+ * only, kernels.py:225-226).  Elements in skipped tiles are copied from S. */
+int npw_syrk_lower_f64(double* C_out, int64_t ldc,
+                       const double* S, int64_t lds,
+                       const double* X, int64_t ldx,
+                       const double* Y, int64_t ldy,
+                       int64_t m, int64_t n, int64_t k, npw_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * kernels.gemm(A, B, transpose_A=False, transpose_B=False) = op(A).dot(op(B))
  *                                                   (kernels.py:239-244)
@@ -159,6 +169,14 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt,
  * op): counter-based uniform(-1,1) fill, reproducible from (seed, row, col). */
 int npw_fill_random_f64(double* A, int64_t lda, int64_t rows, int64_t cols,
                         uint64_t seed, int64_t row0, int64_t col0,
+                        npw_stream_t stream);
+
+/* Diagnostic used by bench.py for the roofline denominator: a register-only loop of
+ * independent DMMA.8x8x4 instructions on every SM (`warps_per_sm` warps x `iters`
+ * iterations x 16 accumulator tiles).  *flops_out (host) receives the flops issued.
+ * `scratch`: npw_fp64_pipe_probe_bytes(warps_per_sm) bytes of device memory. */
+size_t npw_fp64_pipe_probe_bytes(int warps_per_sm);
+int npw_fp64_pipe_probe(double* scratch, int iters, int warps_per_sm, double* flops_out,
                         npw_stream_t stream);
 
 /* Number of kernel launches this library has enqueued since load (all threads);

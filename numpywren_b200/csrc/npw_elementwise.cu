@@ -143,6 +143,25 @@ __global__ void __launch_bounds__(EW_THREADS) fill_random_kernel(double* A, int6
   }
 }
 
+// Register-only DMMA issue loop: the fp64 tensor pipe's attainable rate (roofline denominator).
+__global__ void __launch_bounds__(512) dmma_probe_kernel(double* out, int iters, double a0, double b0) {
+  double c[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+  const double a = a0 + threadIdx.x * 1e-9, b = b0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[i][0]), "+d"(c[i][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  out[static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x] = s;
+}
+
 template <int COUNT>
 int launch_addn(double* out, const PtrPack& pk, int64_t nelem, int vec, cudaStream_t st) {
   addn_kernel<COUNT><<<ew_grid(nelem, 8), EW_THREADS, 0, st>>>(out, pk, nelem, vec);
@@ -245,6 +264,27 @@ int npw_fill2d_f64(double* A, int64_t lda, int64_t rows, int64_t cols, int mode,
   if (lda < cols) return -2;
   if (mode < 0 || mode > 2) return -5;
   return npw::launch_fill2d(A, lda, rows, cols, mode, value, static_cast<cudaStream_t>(stream));
+}
+
+size_t npw_fp64_pipe_probe_bytes(int warps_per_sm) {
+  if (warps_per_sm < 1 || warps_per_sm > 16) return 0;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+  return static_cast<size_t>(sms) * warps_per_sm * 32 * sizeof(double);
+}
+
+int npw_fp64_pipe_probe(double* scratch, int iters, int warps_per_sm, double* flops_out, npw_stream_t stream) {
+  if (!scratch) return -1;
+  if (iters < 1) return -2;
+  if (warps_per_sm < 1 || warps_per_sm > 16) return -3;
+  int dev = 0, sms = 0;
+  NPW_CUDA_CHECK(cudaGetDevice(&dev));
+  NPW_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  npw::dmma_probe_kernel<<<sms, warps_per_sm * 32, 0, static_cast<cudaStream_t>(stream)>>>(scratch, iters, 1.0, 1.0);
+  NPW_LAUNCH_CHECK();
+  if (flops_out) *flops_out = 2.0 * 256.0 * 16.0 * iters * warps_per_sm * sms;
+  return NPW_OK;
 }
 
 int npw_fill_random_f64(double* A, int64_t lda, int64_t rows, int64_t cols, uint64_t seed, int64_t row0, int64_t col0,

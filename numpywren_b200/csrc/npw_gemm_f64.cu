@@ -70,7 +70,17 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     tile_m = first_m + r % gm;
     tile_n = r / gm;
   }
-  if (p.lower_only && tile_n * BN > tile_m * BM + (BM - 1)) return;
+  if (p.lower_only && tile_n * BN > tile_m * BM + (BM - 1)) {
+    // tile strictly above the diagonal: not computed.  Out of place, C0 is passed through so that the
+    // output tile is fully defined (in place there is nothing to do).
+    if (p.C0 != nullptr && p.C0 != p.C) {
+      for (int e = threadIdx.x; e < BM * BN; e += NTHREADS) {
+        const int r = tile_m * BM + e / BN, c = tile_n * BN + e % BN;
+        if (r < p.m && c < p.n) p.C[static_cast<int64_t>(r) * p.ldc + c] = p.C0[static_cast<int64_t>(r) * p.ldc0 + c];
+      }
+    }
+    return;
+  }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -196,7 +206,15 @@ gemm_generic_kernel(double* __restrict__ C, int64_t ldc, const double* C0, int64
   __shared__ double As[GK][GB + 1];
   __shared__ double Bs[GK][GB + 1];
   const int bm = blockIdx.y * GB, bn = blockIdx.x * GB;
-  if (lower_only && bn > bm + GB - 1) return;
+  if (lower_only && bn > bm + GB - 1) {
+    if (C0 != nullptr && C0 != C) {
+      for (int e = threadIdx.x; e < GB * GB; e += 256) {
+        const int r = bm + e / GB, c = bn + e % GB;
+        if (r < m && c < n) C[static_cast<int64_t>(r) * ldc + c] = C0[static_cast<int64_t>(r) * ldc0 + c];
+      }
+    }
+    return;
+  }
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   double acc[4][4] = {};
   for (int k0 = 0; k0 < k; k0 += GK) {
@@ -319,6 +337,7 @@ extern "C" {
 
 int npw_syrk_f64(double* C_out, int64_t ldc, const double* S, int64_t lds, const double* X, int64_t ldx,
                  const double* Y, int64_t ldy, int64_t m, int64_t n, int64_t k, npw_stream_t stream) {
+  if (m == 0 || n == 0) return NPW_OK;  // empty tile: nothing to enqueue
   if (!C_out) return -1;
   if (ldc < n) return -2;
   if (!S) return -3;
@@ -334,9 +353,28 @@ int npw_syrk_f64(double* C_out, int64_t ldc, const double* S, int64_t lds, const
                           static_cast<cudaStream_t>(stream));
 }
 
+int npw_syrk_lower_f64(double* C_out, int64_t ldc, const double* S, int64_t lds, const double* X, int64_t ldx,
+                       const double* Y, int64_t ldy, int64_t m, int64_t n, int64_t k, npw_stream_t stream) {
+  if (m == 0 || n == 0) return NPW_OK;
+  if (!C_out) return -1;
+  if (ldc < n) return -2;
+  if (!S) return -3;
+  if (lds < n) return -4;
+  if (!X && k > 0) return -5;
+  if (ldx < k) return -6;
+  if (!Y && k > 0) return -7;
+  if (ldy < k) return -8;
+  if (m < 0) return -9;
+  if (n < 0) return -10;
+  if (k < 0) return -11;
+  return npw::launch_gemm(C_out, ldc, S, lds, X, ldx, 0, Y, ldy, 1, m, n, k, -1.0, 1.0, 1,
+                          static_cast<cudaStream_t>(stream));
+}
+
 int npw_gemm_f64(double* C, int64_t ldc, const double* C0, int64_t ldc0, const double* A, int64_t lda, int transA,
                  const double* B, int64_t ldb, int transB, int64_t m, int64_t n, int64_t k, double alpha, double beta,
                  npw_stream_t stream) {
+  if (m == 0 || n == 0) return NPW_OK;
   if (!C) return -1;
   if (ldc < n) return -2;
   if (beta != 0.0 && C0 && ldc0 < n) return -4;

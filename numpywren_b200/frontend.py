@@ -42,9 +42,14 @@ class _Log:
         a, b = self.x, other.x
         approx = math.log(a) / math.log(b)
         if isinstance(a, int) and isinstance(b, int) and b > 1 and a >= 1:
-            r = int(round(approx))
-            if r >= 0 and b ** r == a:
+            # exact integer part: largest r with b**r <= a; the float quotient only supplies the fraction
+            r, p = 0, 1
+            while p * b <= a:
+                p *= b
+                r += 1
+            if p == a:
                 return r
+            return r + min(max(approx - r, 1e-9), 1.0 - 1e-9)
         return approx
 
     def __truediv__(self, other):

@@ -120,6 +120,8 @@ class TileEngine:
         self.input_names = set(self.compiled.inputs)
         self._input_mats = {id(self.compiled.scope[n]) for n in self.input_names if n in self.compiled.scope}
         self._prio: Optional[List[int]] = None
+        self._lower_ok: Dict[int, bool] = {}
+        self.skip_upper = os.environ.get("NPW_B200_SKIP_UPPER", "1") != "0"
 
     # ------------------------------------------------------------------ priorities
     def priorities(self) -> List[int]:
@@ -139,6 +141,26 @@ class TileEngine:
                         stack.append(p)
             self._prio = prio
         return self._prio
+
+    def _only_feeds_lower_readers(self, node) -> bool:
+        """True when every consumer of this node's output is chol or another same-operand (diagonal) syrk."""
+        ok = self._lower_ok.get(node.nid)
+        if ok is None:
+            ok = True
+            for c in node.children:
+                ch = self.compiled.nodes[c]
+                if ch.call.compute is kernels.chol:
+                    continue
+                if ch.call.compute is kernels.syrk and len(ch.reads) == 3 and \
+                        _tile_key(*ch.reads[1]) == _tile_key(*ch.reads[2]) and \
+                        _tile_key(*ch.reads[0]) == _tile_key(*node.writes[0]) and self._only_feeds_lower_readers(ch):
+                    continue  # the next diagonal update also ignores (and never exposes) the upper triangle
+                ok = False
+                break
+            if not node.children:
+                ok = False  # a sink's tile is user-visible: compute all of it
+            self._lower_ok[node.nid] = ok
+        return ok
 
     # ------------------------------------------------------------------ plumbing
     def _ensure_device(self, tensor_device: torch.device):
@@ -182,6 +204,12 @@ class TileEngine:
     def _read(self, m, idx, stream):
         """→ (2-D/N-D tile tensor, stored_ref_or_None, tile_key).  Never copies unless lambdav/transposed views force it."""
         key = _tile_key(m, idx)
+        if self.comm is not None and self.comm.grid.owner(m, idx) != self.comm.rank:
+            buf = self.comm.remote_tile(key, stream)
+            if buf is None:
+                raise Exception("tile {0}{1} lives on rank {2} and was never received".format(
+                    m.key, list(idx), self.comm.grid.owner(m, idx)))
+            return (buf.squeeze() if m.autosqueeze else buf), None, key, False
         self._wait_tile(key, stream)
         ref = m._get_block_ref(*idx) if hasattr(m, "_get_block_ref") else None
         shifted = (len(set(idx)) == 1 and len(set(m.shape)) == 1 and len(m.shape) != 1 and m.lambdav != 0)
@@ -239,7 +267,10 @@ class TileEngine:
             if fn is kernels.syrk and len(args) == 3:
                 out = args[0] if can_overwrite(0) else None
                 consumed = 0 if out is not None else None
-                results = kernels.syrk(args[0], args[1], args[2], out=out)
+                # a diagonal tile S[i,j,j] = S - L_j L_j^T feeds only chol (lower triangle) or the next diagonal
+                # syrk: the CTA tiles strictly above the diagonal are skipped (half the flops of these tasks)
+                diag = self.skip_upper and keys[1] == keys[2] and self._only_feeds_lower_readers(node)
+                results = kernels.syrk(args[0], args[1], args[2], out=out, lower=diag)
             elif fn is kernels.trsm and len(args) == 2:
                 out = args[1] if can_overwrite(1) else None
                 consumed = 1 if out is not None else None
@@ -288,6 +319,8 @@ class TileEngine:
     # ------------------------------------------------------------------ drain
     def finish(self):
         """Wait for the device and surface asynchronous kernel failures (LAPACK-style info codes)."""
+        if self.comm is not None:
+            self.comm.drain()
         if self.device is not None:
             torch.cuda.synchronize(self.device)
         bad = []
@@ -296,12 +329,24 @@ class TileEngine:
             if code != 0:
                 bad.append((node, code))
         self.infos = []
+        if self.comm is not None:
+            # every rank must agree on failure: share the smallest failing node id (or "none")
+            from . import parallel
+            mine = min((n.nid for n, _ in bad), default=-1)
+            worst = parallel.allreduce_max_int(-1 if mine < 0 else (1 << 40) - mine, self.device or torch.device("cuda"))
+            if worst >= 0 and not bad:
+                nid = (1 << 40) - worst
+                bad = [(self.compiled.nodes[nid], -1)]
         return bad
 
 
 def _engine_for(program: lp.LambdaPackProgram, **opts) -> TileEngine:
     eng = getattr(program, "_engine", None)
     if eng is None:
+        from . import parallel
+        grid = parallel.current_grid()
+        if grid is not None and grid.world > 1:
+            opts["comm"] = parallel.TileExchange(program.program, grid)
         eng = TileEngine(program, **opts)
         program._engine = eng
         prio = eng.priorities()
@@ -353,7 +398,13 @@ def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, 
                     if status == lp.NS.RUNNING:
                         program.incr_repeated_compute()
                     program.set_node_status(expr_idx, var_values, lp.NS.RUNNING)
-                    eng.run_node(node)
+                    comm = eng.comm
+                    if comm is not None:
+                        comm.before_node(node, eng)
+                    if comm is None or comm.exec_rank(node) == comm.rank:
+                        eng.run_node(node)
+                    if comm is not None:
+                        comm.after_node(node, eng)
                 else:
                     program.incr_repeated_post_op()
                 program.post_op(expr_idx, var_values, lp.PS.SUCCESS, None)

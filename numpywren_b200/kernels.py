@@ -135,8 +135,9 @@ def _out_tile(out, shape, device, name):
     return out
 
 
-def syrk(s, x, y, *args, out=None, **kwargs):
-    """s - x.dot(y.T)  — kernels.py:212-215.  ``out`` (scheduler use) may be ``s`` itself: in-place update."""
+def syrk(s, x, y, *args, out=None, lower=False, **kwargs):
+    """s - x.dot(y.T)  — kernels.py:212-215.  ``out`` (scheduler use) may be ``s`` itself: in-place update.
+    ``lower=True`` (scheduler use, diagonal tiles) updates only the CTA tiles touching the lower triangle."""
     _check_tile(s, "s")
     _check_tile(x, "x")
     _check_tile(y, "y")
@@ -149,8 +150,9 @@ def syrk(s, x, y, *args, out=None, **kwargs):
     if not x_t and not y_t:
         if x.shape[1] != y.shape[1]:
             raise ValueError(f"shapes {tuple(x.shape)} and {tuple(y.T.shape)} not aligned")
-        rc = _capi.load().npw_syrk_f64(out.data_ptr(), out.stride(0), sm.data_ptr(), sm.stride(0), xm.data_ptr(), ldx,
-                                       ym.data_ptr(), ldy, x.shape[0], y.shape[0], x.shape[1], _stream())
+        fn = _capi.load().npw_syrk_lower_f64 if lower else _capi.load().npw_syrk_f64
+        rc = fn(out.data_ptr(), out.stride(0), sm.data_ptr(), sm.stride(0), xm.data_ptr(), ldx,
+                ym.data_ptr(), ldy, x.shape[0], y.shape[0], x.shape[1], _stream())
         _capi.check(rc, "npw_syrk_f64")
         return out
     return _gemm_into(out, sm, x, y, False, True, -1.0, 1.0)

@@ -257,6 +257,12 @@ class BigMatrix(object):
             val = pf(self, *block_idx)
         return self._to_tile(val) if not (isinstance(val, torch.Tensor) and val.device == self.device) else val
 
+    def _is_local(self, block_idx) -> bool:
+        """With several processes (one per GPU) a tile lives only on its owner rank (parallel.ProcessGrid)."""
+        from . import parallel
+        grid = parallel.current_grid()
+        return grid is None or grid.world == 1 or grid.owner(self, block_idx) == grid.rank
+
     def _get_block_ref(self, *block_idx):
         """Stored tensor itself (no copy, no squeeze, no lambdav) or None.  Scheduler-internal."""
         return self._blocks_store.get(tuple(int(i) for i in block_idx))
@@ -276,6 +282,10 @@ class BigMatrix(object):
             raise Exception("Get block query does not match shape {0} vs {1}".format(block_idx, self.shape))
         block_idx = tuple(int(i) for i in block_idx)
         stored = self._blocks_store.get(block_idx)
+        if stored is None and not self._is_local(block_idx):
+            from . import parallel
+            raise Exception("tile {0}{1} is owned by rank {2}; use numpy() (collective) or run it through a program".format(
+                self.key, list(block_idx), parallel.current_grid().owner(self, block_idx)))
         if stored is None:
             X_block = self._default_block(block_idx)
             if X_block is None:
@@ -312,6 +322,8 @@ class BigMatrix(object):
                 shape = current_shape
         if self.safe and shape != current_shape:
             raise Exception("{2} Incompatible block size: {0} vs {1}".format(shape, current_shape, self))
+        if not self._is_local(block_idx):
+            return None   # SPMD: every rank issues the same put, only the tile's owner stores it
         self._blocks_store[block_idx] = self._to_tile(block)
         return None
 

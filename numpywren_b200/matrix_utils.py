@@ -33,6 +33,10 @@ def make_constant_parent(cnst):
 
 def get_local_matrix(bigm, workers=None):
     """All tiles → one host ndarray.  Tiles that were never written come from ``parent_fn``."""
+    from . import parallel
+    grid = parallel.current_grid()
+    if grid is not None and grid.world > 1:
+        return parallel.gather_numpy(bigm)
     out = np.zeros(tuple(bigm.shape), dtype=bigm.dtype)
     tout = torch.from_numpy(out)
     for bidx, blk in zip(bigm._block_idxs(), bigm._blocks()):

@@ -1,0 +1,382 @@
+"""Multi-GPU execution: one process per GPU, tiles sharded by block index, panel tiles exchanged over NVLink.
+
+The reference scales by letting any stateless worker read any tile from S3 (README "S3 as distributed
+memory"; lambdapack.py:257,319).  On one 8xB200 box the equivalent of the object store is the union of the
+GPUs' HBM: every tile has ONE owner rank (2-D block-cyclic over its block index, like ScaLAPACK/SLATE, which
+keeps the shrinking trailing matrix of a factorisation balanced), the owner of a node's output tile executes
+the node ("owner computes"), and a tile needed by another rank is pushed to it over NVLink/NVSwitch as soon as
+it exists.  All ranks walk the SAME expanded DAG in the SAME order (SPMD), so the set and order of transfers is
+known on both sides without any control messages: the sender posts an NCCL send right after the producing
+kernel, the receiver posts the matching recv, and consumers wait on the receive like on any other tile event.
+
+The exchange step of blocked Cholesky is exactly one pattern: panel tile O[j,i] (and O[i,i]) goes to the owners
+of row j / column j of the trailing matrix.  Nothing else crosses GPUs; there is no data-path collective.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+_GRID: Optional["ProcessGrid"] = None
+
+
+def factor_grid(world: int) -> Tuple[int, int]:
+    """P x Q with P <= Q and P*Q == world, as square as possible (8 -> 2x4, 4 -> 2x2, 2 -> 1x2)."""
+    p = int(np.floor(np.sqrt(world)))
+    while world % p:
+        p -= 1
+    return p, world // p
+
+
+class ProcessGrid:
+    """Rank layout and tile ownership."""
+
+    def __init__(self, world: int, rank: int, shape: Optional[Tuple[int, int]] = None):
+        self.world, self.rank = int(world), int(rank)
+        self.P, self.Q = shape if shape is not None else factor_grid(self.world)
+        if self.P * self.Q != self.world:
+            raise ValueError(f"grid {self.P}x{self.Q} does not match world size {self.world}")
+
+    def coords(self, matrix, idx) -> Tuple[int, int]:
+        """The two block coordinates that decide ownership.  A matrix may carry its own ``placement(idx)``;
+        by default: 2-D → (i, j); 3-D (SSA version first, e.g. Cholesky's S[v, j, k]) → (j, k); 4-D (GEMM's
+        Temp[i, j, k, level]) → (i, j); 1-D → (i, 0)."""
+        true = matrix.true_block_idx(*idx) if hasattr(matrix, "true_block_idx") else tuple(idx)
+        fn = getattr(matrix, "placement", None)
+        if fn is not None:
+            return fn(true)
+        nd = len(true)
+        if nd == 1:
+            return int(true[0]), 0
+        if nd == 2:
+            return int(true[0]), int(true[1])
+        if nd == 3:
+            return int(true[1]), int(true[2])
+        return int(true[0]), int(true[1])
+
+    def owner(self, matrix, idx) -> int:
+        a, b = self.coords(matrix, idx)
+        return (a % self.P) * self.Q + (b % self.Q)
+
+    def is_mine(self, matrix, idx) -> bool:
+        return self.owner(matrix, idx) == self.rank
+
+
+def set_grid(grid: Optional[ProcessGrid]):
+    global _GRID
+    _GRID = grid
+
+
+def current_grid() -> Optional[ProcessGrid]:
+    return _GRID
+
+
+def init_from_env(backend: Optional[str] = None) -> ProcessGrid:
+    """Join the torchrun rendezvous (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*), bind this process to its GPU and
+    install the process grid.  backend defaults to nccl when CUDA is visible, gloo otherwise (CPU host-logic tests)."""
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        kw = {}
+        if backend == "nccl":
+            kw["device_id"] = torch.device("cuda", local)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+    grid = ProcessGrid(world, rank)
+    set_grid(grid)
+    return grid
+
+
+# ------------------------------------------------------------------------------------------- transfer plan
+class TransferPlan:
+    """Who needs which tile, derived from the expanded DAG (identical on every rank).
+
+    For every tile read by a node executed on a rank other than the tile's owner there is exactly one transfer
+    (tile, owner → that rank).  ``after_node[nid]`` lists the transfers triggered by node nid's outputs;
+    ``before_node[nid]`` lists transfers of pre-existing tiles (program inputs) first needed by node nid.
+    """
+
+    def __init__(self, compiled, grid: ProcessGrid):
+        from .compiler import _tile_key
+        self.grid = grid
+        nodes = compiled.nodes
+        self.exec_rank = [grid.owner(*n.writes[0]) for n in nodes]
+        self.after_node: Dict[int, List[Tuple[Any, Any, Tuple[int, ...], int, int]]] = {}
+        self.before_node: Dict[int, List[Tuple[Any, Any, Tuple[int, ...], int, int]]] = {}
+        self.last_use: Dict[Tuple[Any, int], int] = {}       # (tile_key, rank) -> last consumer nid on that rank
+        seen = set()
+        for n in nodes:
+            dst = self.exec_rank[n.nid]
+            for (m, idx) in n.reads:
+                key = _tile_key(m, idx)
+                src = grid.owner(m, idx)
+                if src == dst:
+                    continue
+                self.last_use[(key, dst)] = n.nid
+                if (key, dst) in seen:
+                    continue
+                seen.add((key, dst))
+                w = compiled.writer_of(m, idx)
+                if w is not None:
+                    self.after_node.setdefault(w.nid, []).append((key, m, tuple(idx), src, dst))
+                else:
+                    self.before_node.setdefault(n.nid, []).append((key, m, tuple(idx), src, dst))
+        self.num_transfers = len(seen)
+
+    def describe(self, rank: int) -> List[Tuple[str, Any, int]]:
+        """Ordered communication script of one rank: [("send"|"recv", tile_key, peer)] — used by the tests to check
+        that every send has a matching recv in the same relative order."""
+        out = []
+        n_nodes = len(self.exec_rank)
+        for nid in range(n_nodes):
+            for lst in (self.before_node.get(nid, ()),):
+                for key, _, _, src, dst in lst:
+                    if src == rank:
+                        out.append(("send", key, dst))
+                    elif dst == rank:
+                        out.append(("recv", key, src))
+            for key, _, _, src, dst in self.after_node.get(nid, ()):
+                if src == rank:
+                    out.append(("send", key, dst))
+                elif dst == rank:
+                    out.append(("recv", key, src))
+        return out
+
+
+class TileExchange:
+    """Posts the planned sends/recvs with torch.distributed P2P (NCCL over NVLink) as the engine walks the DAG."""
+
+    def __init__(self, compiled, grid: ProcessGrid):
+        self.grid = grid
+        self.rank = grid.rank
+        self.plan = TransferPlan(compiled, grid)
+        self.cache: Dict[Any, Tuple[torch.Tensor, Any]] = {}   # tile_key -> (buffer, recv work)
+        self.pending_sends: List[Any] = []
+        self.bytes_sent = 0
+        self.bytes_received = 0
+
+    def exec_rank(self, node) -> int:
+        return self.plan.exec_rank[node.nid]
+
+    def _do(self, transfers, engine, node_order_hint=None):
+        import torch.distributed as dist
+        for key, m, idx, src, dst in transfers:
+            if src == self.rank:
+                ref = m._get_block_ref(*idx)
+                if ref is None:
+                    tile = m.get_block(*idx)       # default (parent_fn) tile of an input matrix
+                else:
+                    tile = ref
+                ev = engine.tile_event.get(key)
+                stream = ev[1] if ev is not None else torch.cuda.current_stream()
+                with torch.cuda.stream(stream):
+                    # issued on the producer's stream: NCCL orders the send after the kernel that wrote the tile
+                    self.pending_sends.append((dist.isend(tile.contiguous(), dst), tile))
+                self.bytes_sent += tile.numel() * tile.element_size()
+            elif dst == self.rank:
+                shape = m.block_shape(*idx)
+                buf = torch.empty(shape, dtype=m.torch_dtype, device=engine.device or m.device)
+                work = dist.irecv(buf, src)
+                self.cache[key] = (buf, work)
+                self.bytes_received += buf.numel() * buf.element_size()
+
+    def before_node(self, node, engine):
+        t = self.plan.before_node.get(node.nid)
+        if t:
+            self._do(t, engine)
+
+    def after_node(self, node, engine):
+        t = self.plan.after_node.get(node.nid)
+        if t:
+            self._do(t, engine)
+        # receive buffers whose last local consumer has been enqueued can go back to the allocator
+        for (m, idx) in node.reads:
+            from .compiler import _tile_key
+            key = _tile_key(m, idx)
+            if key in self.cache and self.plan.last_use.get((key, self.rank)) == node.nid:
+                del self.cache[key]
+
+    def remote_tile(self, key, stream) -> Optional[torch.Tensor]:
+        ent = self.cache.get(key)
+        if ent is None:
+            return None
+        buf, work = ent
+        with torch.cuda.stream(stream):
+            work.wait()                 # stream-level wait on the NCCL receive, the host does not block
+        buf.record_stream(stream)
+        return buf
+
+    def drain(self):
+        for work, _ in self.pending_sends:
+            work.wait()
+        self.pending_sends = []
+        self.cache.clear()
+
+
+# ------------------------------------------------------------------------------------------- collectives on BigMatrix
+def gather_numpy(bigm) -> np.ndarray:
+    """Collective: every rank receives the whole matrix as a host ndarray (owner broadcasts each tile)."""
+    import torch.distributed as dist
+    grid = current_grid()
+    out = np.zeros(tuple(bigm.shape), dtype=bigm.dtype)
+    tout = torch.from_numpy(out)
+    dev = bigm.device
+    for bidx, blk in zip(bigm._block_idxs(), bigm._blocks()):
+        sl = tuple(slice(s, e) for s, e in blk)
+        owner = grid.owner(bigm, bidx)
+        shape = tuple(e - s for s, e in blk)
+        have = torch.zeros(1, dtype=torch.int32, device=dev)
+        if owner == grid.rank:
+            ref = bigm._get_block_ref(*bidx)
+            if ref is not None or bigm.parent_fn is not None:
+                have += 1
+        dist.broadcast(have, src=owner)
+        if int(have.item()) == 0:
+            raise Exception("Key does {0} not exist, and no parent function prescripted".format(bigm.__shard_idx_to_key__(bidx)))
+        if owner == grid.rank:
+            tile = bigm.get_block(*bidx).reshape(shape).contiguous()
+        else:
+            tile = torch.empty(shape, dtype=bigm.torch_dtype, device=dev)
+        dist.broadcast(tile, src=owner)
+        tout[sl].copy_(tile.cpu())
+    return out
+
+
+def allreduce_max_int(value: int, device) -> int:
+    import torch.distributed as dist
+    t = torch.tensor([int(value)], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return int(t.item())
+
+
+# ------------------------------------------------------------------------------------------- bench (N > 1)
+def bench_main(args, metric, unit, workload):
+    """bench.py --gpus N (N>1): each rank generates and factors its block-cyclic share of the same global matrix."""
+    import json
+    import sys
+    import time
+    import torch.distributed as dist
+    from . import _capi, job_runner, kernels
+    from . import lambdapack as lp
+    from .alg_wrappers import cholesky
+    from .matrix import BigMatrix
+
+    grid = init_from_env("nccl")
+    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    _capi.load()
+    n, b = args.n, args.tile
+    nb = n // b
+    X = [torch.empty(b, 128, dtype=torch.float64, device=device) for _ in range(nb)]
+    for j in range(nb):
+        kernels.fill_random(X[j], seed=20261017, row0=j * b)
+
+    def make_input(step):
+        A = BigMatrix(f"bench_A_{step}", shape=(n, n), shard_sizes=(b, b), device=device)
+        for j in range(nb):
+            for k in range(j + 1):
+                if grid.is_mine(A, (j, k)):
+                    t = torch.empty(b, b, dtype=torch.float64, device=device)
+                    kernels._gemm_into(t, None, X[j], X[k], False, True, 1.0, 0.0)
+                    if j == k:
+                        kernels.add_diag(t, float(n))
+                    A._put_block_ref(t, j, k)
+        return A
+
+    def step(i):
+        A = make_input(i)
+        program, meta = cholesky(A)
+        _ = program.program.nodes
+        torch.cuda.synchronize()
+        dist.barrier()
+        l0 = _capi.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        program.start()
+        job_runner.lambdapack_run(program, timeout=3600, streams=args.streams, consume_inputs=True)
+        e1.record()
+        e1.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        launches = torch.tensor([_capi.launch_count() - l0], dtype=torch.int64, device=device)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+        assert program.program_status() == lp.PS.SUCCESS
+        eng = program._engine
+        sent = eng.comm.bytes_sent if eng.comm is not None else 0
+        return float(ms.item()), int(launches.item()), A, program, meta, sent
+
+    def residual(meta):
+        """||(L L^T)_jk - A_jk|| / ||A_jk|| on the last diagonal tile, computed by its owner from gathered row tiles."""
+        O = meta["outputs"][0]
+        j = nb - 1
+        owner = grid.owner(O, (j, j))
+        acc = torch.zeros(b, b, dtype=torch.float64, device=device)
+        for i in range(j + 1):
+            src = grid.owner(O, (j, i))
+            t = O._get_block_ref(j, i) if src == grid.rank else torch.empty(b, b, dtype=torch.float64, device=device)
+            dist.broadcast(t, src=src)
+            if grid.rank == owner:
+                kernels._gemm_into(acc, acc, t, t, False, True, 1.0, 1.0)
+        val = torch.zeros(1, dtype=torch.float64, device=device)
+        if grid.rank == owner:
+            ref = torch.empty(b, b, dtype=torch.float64, device=device)
+            kernels._gemm_into(ref, None, X[j], X[j], False, True, 1.0, 0.0)
+            kernels.add_diag(ref, float(n))
+            val[0] = (acc - ref).norm() / ref.norm()
+        dist.broadcast(val, src=owner)
+        return float(val.item())
+
+    def free_all(A, meta):
+        for m in [A] + meta["outputs"] + meta["intermediates"]:
+            m.free()
+
+    resid, sent = None, 0
+    for w in range(args.warmup):
+        ms, _, A, program, meta, sent = step(f"w{w}")
+        if grid.rank == 0:
+            print(f"warmup {w}: {ms:.1f} ms", file=sys.stderr, flush=True)
+        if w == args.warmup - 1:
+            resid = residual(meta)
+        free_all(A, meta)
+        del A, program, meta
+    sampler = None
+    if grid.rank == 0:
+        from bench import ClockSampler  # the driver runs bench.py as __main__ from the repo root
+        sampler = ClockSampler(index=int(os.environ.get("LOCAL_RANK", "0")))
+        sampler.start()
+    times, launches_tot = [], 0
+    for s in range(args.steps):
+        ms, launches, A, program, meta, sent = step(f"s{s}")
+        times.append(ms)
+        launches_tot += launches
+        free_all(A, meta)
+        del A, program, meta
+    clocks = sampler.stop() if sampler is not None else None
+    ms_per_step = float(np.mean(times))
+    value = (n ** 3 / 3.0) / (ms_per_step * 1e-3) * 1e-12
+    sent_t = torch.tensor([sent], dtype=torch.int64, device=device)
+    dist.all_reduce(sent_t, op=dist.ReduceOp.SUM)
+    if grid.rank == 0:
+        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": grid.world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": workload, "process_grid": f"{grid.P}x{grid.Q} block-cyclic over tile index",
+                           "tile_tasks": nb * (nb + 1) * (nb + 2) // 6, "streams": args.streams,
+                           "l2": "inputs larger than L2; every step regenerates its input",
+                           "nvlink_bytes_per_step": int(sent_t.item()), "residual_LLt_minus_A": resid,
+                           "algorithmic_flops_per_step": n ** 3 / 3.0},
+                "roofline": None, "cpu_baseline": None,
+                "e2e": {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                        "note": "host-buffer end-to-end is measured at N=1 only"},
+                "gpu_launches": launches_tot, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+    return 0

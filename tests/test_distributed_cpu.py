@@ -1,0 +1,66 @@
+"""Host-side logic of the multi-GPU path on CPU: world_size 2 and 4 over gloo (tile ownership, SPMD puts, collective
+gather, and the NVLink transfer plan derived from the DAG)."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+from numpywren_b200 import parallel
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gloo_world(world):
+    port = free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), NPW_B200_DEVICE="cpu", OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_dist_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{out[-3000:]}"
+    assert "DIST_OK %d" % world in outs[0]
+
+
+def test_grid_shapes_and_ownership():
+    assert parallel.factor_grid(1) == (1, 1)
+    assert parallel.factor_grid(2) == (1, 2)
+    assert parallel.factor_grid(4) == (2, 2)
+    assert parallel.factor_grid(8) == (2, 4)
+    assert parallel.factor_grid(6) == (2, 3)
+
+    class M:
+        def true_block_idx(self, *idx):
+            return idx
+    g = parallel.ProcessGrid(8, 3)
+    assert g.owner(M(), (0, 0)) == 0 and g.owner(M(), (1, 0)) == 4 and g.owner(M(), (1, 3)) == 7
+    assert g.owner(M(), (5, 2, 6)) == g.owner(M(), (2, 6))          # SSA version axis does not move a tile
+    assert g.owner(M(), (3,)) == (3 % 2) * 4
+    counts = [0] * 8
+    for j in range(32):
+        for k in range(j + 1):
+            counts[g.owner(M(), (j, k))] += 1
+    assert max(counts) - min(counts) <= 16 and min(counts) >= 56      # block-cyclic balances the lower triangle
+    with pytest.raises(ValueError):
+        parallel.ProcessGrid(8, 0, shape=(3, 3))

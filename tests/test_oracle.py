@@ -1,0 +1,117 @@
+"""The CPU oracle (oracle/npw_oracle.py) against fixtures produced by the UNMODIFIED reference
+(oracle/make_golden.py).  CPU only."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import npw_oracle as orc
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def test_kernels_match_reference(golden_dir):
+    g = _load(golden_dir, "kernels.npz")
+    assert np.array_equal(orc.syrk(g["s"], g["x"], g["y"]), g["syrk"])
+    assert np.array_equal(orc.chol(g["spd"]), g["chol"])
+    assert np.array_equal(orc.trsm(g["chol"], g["trsm_b"]), g["trsm"])
+    assert np.array_equal(orc.add_matrices(g["p0"], g["p1"], g["p2"], g["p3"]), g["add"])
+    assert np.array_equal(orc.gemm(g["ga"], g["gb"]), g["gemm"])
+    assert np.array_equal(orc.mul(g["p0"], g["p1"]), g["mul"])
+
+
+def test_trsm_is_right_solve_with_transposed_lower(golden_dir):
+    g = _load(golden_dir, "kernels.npz")
+    L = g["chol"]
+    np.testing.assert_allclose(orc.trsm(L, g["trsm_b"]), g["trsm_b"] @ np.linalg.inv(L).T, rtol=1e-12, atol=1e-12)
+
+
+def test_syrk_and_trsm_zero_shortcuts():
+    s = np.ones((4, 4))
+    assert orc.syrk(s, np.zeros((4, 3)), np.ones((4, 3))) is s           # kernels.py:213-214
+    z = orc.trsm(np.eye(4), np.zeros((5, 4)))
+    assert z.shape == (4, 5) and not z.any()                              # kernels.py:255-256 (shape quirk)
+
+
+@pytest.mark.parametrize("name", ["cholesky_64_8", "cholesky_64_16", "cholesky_60_16", "cholesky_64_32_lam"])
+def test_cholesky_program_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name + ".npz")
+    n, b, lam = int(g["n"]), int(g["b"]), float(g["lambdav"])
+    I = orc.OracleBigMatrix("A", (n, n), (b, b), lambdav=lam)
+    orc.shard_matrix(I, g["A"])
+    O, S = orc.run_cholesky(I)
+    assert np.array_equal(O.numpy(), g["L"])
+    s_keys = [k for k in g.files if k.startswith("S_")]
+    assert len(s_keys) == len(S.store)
+    for k in s_keys:
+        i, j, kk = (int(x) for x in k.split("_")[1:])
+        assert np.array_equal(S.store[(i, j, kk)].reshape(g[k].shape), g[k])
+    # and the reference's own acceptance criterion (tests/test_alg_correctness.py:47-49)
+    assert np.allclose(O.numpy(), np.linalg.cholesky(g["A"] + lam * np.eye(n)))
+
+
+@pytest.mark.parametrize("name", ["gemm_64_16", "gemm_32_16"])
+def test_gemm_program_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name + ".npz")
+    n, b = int(g["n"]), int(g["b"])
+    A = orc.OracleBigMatrix("A", (n, n), (b, b)); orc.shard_matrix(A, g["A"])
+    B = orc.OracleBigMatrix("B", (n, n), (b, b)); orc.shard_matrix(B, g["B"])
+    Out, _ = orc.run_gemm(A, B)
+    assert np.array_equal(Out.numpy(), g["C"])
+    assert np.allclose(orc.binops_gemm(A, B).numpy(), g["A"] @ g["B"])
+
+
+@pytest.mark.parametrize("name", ["tsqr_256_32", "tsqr_128_16"])
+def test_tsqr_program_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name + ".npz")
+    m, b, nlev = int(g["m"]), int(g["b"]), int(g["nlev"])
+    X = orc.OracleBigMatrix("X", (m, b), (b, b)); orc.shard_matrix(X, g["X"])
+    Rs, Vs, Ts = orc.run_tsqr(X)
+    R = Rs.get_block(nlev, 0)
+    assert np.array_equal(R, g["R"])
+    for k in g.files:
+        if k[:2] in ("R_", "V_") or k.startswith("Tq_"):
+            lvl, j = (int(x) for x in k.split("_")[1:])
+            mat = {"R": Rs, "V": Vs, "Tq": Ts}[k.split("_")[0]]
+            assert np.array_equal(mat.store[(lvl, j)], g[k]), k
+    # reference acceptance criterion: R equals numpy's R up to row signs (tests/test_alg_correctness.py:95-102)
+    Rnp = np.linalg.qr(g["X"])[1]
+    np.testing.assert_allclose(np.abs(R), np.abs(Rnp), rtol=1e-10, atol=1e-12)
+
+
+def test_qr_factor_is_compact_wy():
+    rs = np.random.RandomState(3)
+    a = rs.randn(96, 24)
+    v, t, r = orc.qr_factor(a[:48], a[48:])
+    q = np.eye(96) - v @ t @ v.T
+    np.testing.assert_allclose(q.T @ q, np.eye(96), atol=1e-13)
+    np.testing.assert_allclose((q @ np.vstack([r, np.zeros((72, 24))])), a, atol=1e-12)
+    assert np.allclose(np.tril(r, -1), 0) and np.allclose(np.tril(t, -1), 0)
+    assert np.allclose(np.diag(v), 1) and np.allclose(np.triu(v, 1), 0)
+
+
+def test_bigmatrix_semantics():
+    m = orc.OracleBigMatrix("m", (200, 200), (101, 101), parent_fn=orc.constant_zeros, lambdav=3.0)
+    assert m.num_blocks(0) == 2 and m.block_idx_to_real_idx((1, 1)) == ((101, 200), (101, 200))
+    assert m.get_block(1, 0).shape == (99, 101) and not m.get_block(1, 0).any()
+    d = m.get_block(1, 1)
+    assert d.shape == (99, 99) and np.array_equal(np.diag(d), np.full(99, 3.0))   # lambdav on diagonal reads
+    with pytest.raises(Exception):
+        m.put_block(np.zeros((5, 5)), 0, 0)                                        # safe shape check
+    x = np.arange(200 * 200, dtype=np.float64).reshape(200, 200)
+    m2 = orc.OracleBigMatrix("m2", (200, 200), (101, 101))
+    orc.shard_matrix(m2, x)
+    assert np.array_equal(m2.numpy(), x)
+    with pytest.raises(Exception):
+        orc.OracleBigMatrix("m3", (4, 4), (2, 2)).get_block(0, 0)                  # no parent_fn, missing key
+
+
+def test_spd_generator_is_well_conditioned():
+    b, n = 32, 64
+    A = np.block([[orc.spd_tile(j, k, b, n, width=16) for k in range(2)] for j in range(2)])
+    assert np.allclose(A, A.T)
+    w = np.linalg.eigvalsh(A)
+    assert w.min() > 0 and w.max() / w.min() < 10

@@ -1,0 +1,130 @@
+"""LambdaPackProgram bookkeeping (node status machine, edge sums, terminators, counters) driven through the
+instruction-level API on a storage-only host device.  Only ``identity`` nodes run, so no kernel is needed:
+this is the reference's post_op logic (lambdapack.py:545-639) without Redis/SQS."""
+import numpy as np
+import pytest
+
+from numpywren_b200 import algs, compiler, job_runner
+from numpywren_b200 import lambdapack as lp
+from numpywren_b200.matrix import BigMatrix
+from numpywren_b200.matrix_init import shard_matrix
+
+
+def Chain(A: BigMatrix, B: BigMatrix, C: BigMatrix, N: int):
+    for i in range(N):
+        B[i, 0] = identity(A[i, 0])
+    for i in range(N):
+        for j in range(0, 2):
+            C[i, j] = identity(B[i, 0])
+
+
+def build(unique_key, N=4):
+    X = np.arange(N * 4, dtype=np.float64).reshape(2 * N, 2)
+    A = BigMatrix(unique_key("A"), shape=X.shape, shard_sizes=(2, 2), device="cpu")
+    B = BigMatrix(unique_key("B"), shape=X.shape, shard_sizes=(2, 2), device="cpu")
+    C = BigMatrix(unique_key("C"), shape=(2 * N, 4), shard_sizes=(2, 2), device="cpu")
+    for m in (A, B, C):
+        m.free()
+    shard_matrix(A, X)
+    p = compiler.lpcompile_for_execution(Chain, inputs=["A"], outputs=["C"])(A, B, C, N)
+    return X, A, C, lp.LambdaPackProgram(p)
+
+
+def drain(program, cache=None):
+    """A synchronous worker built from the public pieces: dequeue -> eval_expr -> instrs -> post_op
+    (the status handling of reference job_runner.py:101-135)."""
+    order = []
+    while True:
+        item = program._dequeue()
+        if item is None:
+            break
+        e, v = item
+        if program.get_node_status(e, v) == lp.NS.FINISHED:
+            program.incr_repeated_finish()
+            continue
+        assert program.get_node_status(e, v) == lp.NS.READY
+        program.set_node_status(e, v, lp.NS.RUNNING)
+        ib = program.program.eval_expr(e, v)
+        for ins in ib.instrs:
+            ins.cache = cache
+            ins()
+        program.post_op(e, v, lp.PS.SUCCESS, ib)
+        program.set_node_status(e, v, lp.NS.FINISHED)
+        order.append((e, tuple(sorted(v.items()))))
+    return order
+
+
+def test_status_machine_and_result(unique_key):
+    N = 4
+    X, A, C, program = build(unique_key, N)
+    assert program.program_status() == lp.PS.NOT_STARTED
+    assert len(program.program.nodes) == N + 2 * N
+    assert program.program.num_terminators == 2 * N
+    program.start()
+    assert program.program_status() == lp.PS.RUNNING
+    assert program.queue_depth() == len(program.program.starters) == N
+    order = drain(program, cache=job_runner.LRUCache(4))
+    assert len(order) == 3 * N and len(set(order)) == 3 * N
+    assert program.program_status() == lp.PS.SUCCESS
+    assert program.get_progress() == 3 * N
+    assert np.array_equal(C.numpy(), np.hstack([X, X]))
+    # every first-phase node ran before the nodes that read its tile
+    pos = {k: i for i, k in enumerate(order)}
+    for i in range(N):
+        for j in range(2):
+            assert pos[(0, (("i", i),))] < pos[(1, (("i", i), ("j", j)))]
+
+
+def test_children_become_ready_only_after_all_parents(unique_key):
+    O = BigMatrix(unique_key("O"), shape=(8, 8), shard_sizes=(2, 2), device="cpu")
+    I = BigMatrix(unique_key("I"), shape=(8, 8), shard_sizes=(2, 2), device="cpu")
+    S = BigMatrix(unique_key("S"), shape=(5, 8, 8), shard_sizes=(1, 2, 2), device="cpu")
+    p = compiler.lpcompile_for_execution(algs.CHOLESKY, ["I"], ["O"])(O, I, S, 4, 0)
+    program = lp.LambdaPackProgram(p)
+    program.start()
+    assert program._dequeue() == (0, {})
+    assert program.queue_depth() == 0
+    program.post_op(0, {}, lp.PS.SUCCESS, None)
+    # chol(0) releases the three trsm(j, 0); syrk nodes need two trsm parents each
+    ready = sorted(program._dequeue()[1]["j"] for _ in range(3))
+    assert ready == [1, 2, 3] and program.queue_depth() == 0
+    program.post_op(1, {"j": 1}, lp.PS.SUCCESS, None)
+    assert program.get_node_status(2, {"j": 1, "k": 1}) == lp.NS.READY          # needs only trsm(1)
+    assert program.get_node_status(2, {"j": 2, "k": 1}) == lp.NS.NOT_READY      # needs trsm(1) and trsm(2)
+    program.post_op(1, {"j": 1}, lp.PS.SUCCESS, None)                           # replayed post_op: edges count once
+    assert program.get_node_status(2, {"j": 2, "k": 1}) == lp.NS.NOT_READY
+    program.post_op(1, {"j": 2}, lp.PS.SUCCESS, None)
+    assert program.get_node_status(2, {"j": 2, "k": 1}) == lp.NS.READY
+    assert program.get_node_status(2, {"j": 2, "k": 2}) == lp.NS.READY
+    assert program.program_status() == lp.PS.RUNNING
+
+
+def test_counters_and_stop(unique_key):
+    _, _, _, program = build(unique_key)
+    program.incr_flops(10); program.incr_flops(-5); program.incr_read(7); program.incr_write(3)
+    assert (program.get_flops(), program.get_read(), program.get_write()) == (10, 7, 3)
+    program.decr_flops(4)
+    assert program.get_flops() == 6
+    program.incr_up(2); program.decr_up(1)
+    assert program.get_up() == 1
+    program.start()
+    program.stop()
+    assert program.program_status() == lp.PS.EXCEPTION and "CANCELLED" in program.exceptions[0]
+
+
+def test_engine_refuses_cpu_tiles(unique_key):
+    from numpywren_b200 import _capi
+    _, _, _, program = build(unique_key)
+    program.start()
+    with pytest.raises(_capi.NpwError, match="no CPU execution path"):
+        job_runner.lambdapack_run(program, timeout=5)
+    assert program.program_status() == lp.PS.EXCEPTION
+
+
+def test_lru_cache_and_busy_time():
+    c = job_runner.LRUCache(max_items=2)
+    c["a"] = 1; c["b"] = 2; _ = c["a"]; c["c"] = 3
+    assert "a" in c and "c" in c and "b" not in c
+    with pytest.raises(KeyError):
+        c["b"]
+    assert job_runner.calculate_busy_time([[0, 2], [1, 3], [5, 6]]) == [[0, 3], [5, 6]]
