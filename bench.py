@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — headline benchmark: fp64 TFLOP/s of the LambdaPACK blocked Cholesky on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--n SIZE] [--tile B]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--size N] [--tile B]
 
 One "step" = one complete factorisation of a synthetic SPD matrix A = X X^T + N I through the
 reference-facing surface: alg_wrappers.cholesky(A) → program.start() → job_runner.lambdapack_run(program).
@@ -418,7 +418,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=None, help="matrix size (default 65536 on 1 GPU, 131072 on more)")
+    ap.add_argument("--size", dest="n", type=int, default=None, help="matrix size N (default 65536 on 1 GPU, 131072 on more)")
     ap.add_argument("--tile", type=int, default=4096)
     ap.add_argument("--streams", type=int, default=4)
     ap.add_argument("--cpu-n", dest="cpu_n", type=int, default=16384, help="bounded CPU sample size")

@@ -86,10 +86,9 @@ def init_from_env(backend: Optional[str] = None) -> ProcessGrid:
     if backend == "nccl":
         torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
-        kw = {}
-        if backend == "nccl":
-            kw["device_id"] = torch.device("cuda", local)
-        dist.init_process_group(backend=backend, rank=rank, world_size=world, **kw)
+        # no device_id: with eager communicator init torch serialises unbatched P2P ops on the world
+        # communicator; lazily created per-pair communicators let sends to different peers overlap
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
     grid = ProcessGrid(world, rank)
     set_grid(grid)
     return grid
@@ -295,7 +294,7 @@ def bench_main(args, metric, unit, workload):
         program, meta = cholesky(A)
         _ = program.program.nodes
         torch.cuda.synchronize()
-        dist.barrier()
+        dist.barrier(device_ids=[device.index])
         l0 = _capi.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -377,6 +376,6 @@ def bench_main(args, metric, unit, workload):
                         "note": "host-buffer end-to-end is measured at N=1 only"},
                 "gpu_launches": launches_tot, "clocks": clocks}
         print(json.dumps(line), flush=True)
-    dist.barrier()
+    dist.barrier(device_ids=[device.index])
     dist.destroy_process_group()
     return 0

@@ -171,3 +171,26 @@ def test_profile_timeline(unique_key, cuda_device):
     tl = job_runner.node_timeline(program)
     assert len(tl) == 20 and {t[0] for t in tl} == {"chol", "trsm", "syrk"}
     assert all(e >= s for _, _, s, e, _ in tl)
+
+
+@pytest.mark.parametrize("name", ["tsqr_256_32", "tsqr_128_16"])
+def test_tsqr_golden(golden_dir, unique_key, cuda_device, name):
+    """tests/test_alg_correctness.py:72-102: R of the TSQR tree vs the reference run (elementwise) and vs numpy up to row signs."""
+    from numpywren_b200.alg_wrappers import tsqr
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m, b, nlev = int(g["m"]), int(g["b"]), int(g["nlev"])
+    X = BigMatrix(unique_key(name), shape=(m, b), shard_sizes=(b, b))
+    shard_matrix(X, g["X"])
+    program, meta = tsqr(X)
+    res = run(program)
+    assert len(res["executed_messages"]) == int(g["nnodes"])
+    Rs, Vs, Ts = meta["outputs"]
+    R = Rs.get_block(nlev, 0).cpu().numpy()
+    assert rel(R, g["R"]) < TOL
+    Rnp = np.linalg.qr(g["X"])[1]
+    assert np.allclose(np.abs(R), np.abs(Rnp))
+    for k in g.files:
+        if k[:2] in ("R_", "V_") or k.startswith("Tq_"):
+            lvl, j = (int(x) for x in k.split("_")[1:])
+            mat = {"R": Rs, "V": Vs, "Tq": Ts}[k.split("_")[0]]
+            assert rel(mat.get_block(lvl, j).cpu().numpy(), g[k]) < TOL, k

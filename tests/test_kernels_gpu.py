@@ -227,5 +227,39 @@ def test_benchmark_tile_4096(cuda_device):
     bmat = s.to(cuda_device)
     X = kernels.trsm_with_inverse(L, bmat, inv)
     back = torch.empty_like(a)
-    kernels._gemm_into(back, None, X, L.T.contiguous(), False, True, 1.0, 0.0)   # X L^T = B
+    kernels._gemm_into(back, None, X, L, False, True, 1.0, 0.0)                  # X L^T = B
     assert float((back - bmat).norm() / bmat.norm()) < 1e-13
+
+
+@pytest.mark.parametrize("m,n", [(32, 32), (64, 32), (48, 17), (256, 32), (300, 70), (1024, 128), (4096, 64), (2048, 512)])
+def test_qr_factor_matches_oracle(cuda_device, m, n):
+    """V, T, R of the compact-WY QR against the oracle's LAPACK dgeqrt restatement of kernels.fast_qr."""
+    rs = np.random.RandomState(m + n)
+    a = rs.randn(m, n)
+    V, T, R = kernels.qr_factor(dev(a, cuda_device))
+    v, t, r = orc.qr_factor(a)
+    assert rel(R, r) < TOL and rel(V, v) < TOL and rel(T, t) < TOL
+    Vn, Tn, Rn = V.cpu().numpy(), T.cpu().numpy(), R.cpu().numpy()
+    assert not np.tril(Rn, -1).any() and not np.tril(Tn, -1).any()
+    assert np.array_equal(np.diag(Vn), np.ones(n)) and not np.triu(Vn, 1).any()
+    q = np.eye(m) - Vn @ Tn @ Vn.T
+    assert np.linalg.norm(q.T @ q - np.eye(m)) < 1e-11 * m
+    assert np.linalg.norm(q[:, :n] @ Rn - a) / np.linalg.norm(a) < 1e-13
+
+
+def test_qr_factor_stacks_blocks_like_tsqr_merge(cuda_device):
+    """TSQR merge node: qr_factor(R_left, R_right) on two upper-triangular factors (algs.py:36)."""
+    rs = np.random.RandomState(12)
+    r0, r1 = np.triu(rs.randn(32, 32)), np.triu(rs.randn(32, 32))
+    V, T, R = kernels.qr_factor(dev(r0, cuda_device), dev(r1, cuda_device))
+    v, t, r = orc.qr_factor(r0, r1)
+    assert V.shape == (64, 32) and rel(R, r) < TOL and rel(V, v) < TOL and rel(T, t) < TOL
+
+
+def test_qr_factor_rank_deficient_column(cuda_device):
+    """A column that is already zero below the diagonal gives tau = 0 (H = I), as LAPACK's dlarfg does."""
+    a = np.random.RandomState(13).randn(64, 8)
+    a[1:, 0] = 0.0
+    V, T, R = kernels.qr_factor(dev(a, cuda_device))
+    v, t, r = orc.qr_factor(a)
+    assert rel(R, r) < TOL and rel(V, v) < TOL and rel(T, t) < TOL and float(T[0, 0]) == 0.0
