@@ -30,92 +30,163 @@ constexpr int LDSM = NB + 1;     // padded row stride (doubles) of the shared bl
 constexpr int POTF2_THREADS = 1024;
 constexpr int POTF2_SMEM = NB * LDSM * 8;
 
-// One CTA.  Shared block W[NB][NB+1]:
-//   lower triangle incl. diagonal  : A -> L            (W[i][p], p <= i)
-//   strictly upper, shifted by one : X^T, X = inv(L)   (X[i][t] at W[t][i+1], t <= i)
-// do_factor = 1: Cholesky-factor the block first (potf2); 0: the block already holds L (trtri only).
-// Blocks smaller than NB are padded with the identity.
+// One CTA of 1024 threads factors a 128x128 block AND inverts the factor, with the matrix held in REGISTERS:
+// thread (tx, ty) = (tid & 31, tid >> 5) owns the 4x4 tile rows 4ty..4ty+3, cols 4tx..4tx+3 (lower tiles: tx <= ty).
+// Right-looking, one __syncthreads per column:
+//   loop 1 (Cholesky): the owners of column j publish it (unscaled) in a double-buffered shared vector; every thread
+//           derives d = sqrt(a_jj), 1/d itself and applies the rank-1 update to its register tile (no shared RMW);
+//   loop 2 (inverse X = L^{-1}, forward substitution by rows): the owners of row j of X publish it; every thread
+//           updates X[i][t] -= L[i][j] * X[j][t] / L_jj in registers, reading column j of L from shared memory.
+// do_factor = 0: the block already holds L (batched trtri of an existing factor).  Blocks smaller than NB are
+// padded with the identity.  Shared: L as W[NB][NB+1] (132 KB) + two small vectors.
+__device__ __forceinline__ void block_chol_inv(double* W, const double* Ain, int64_t lda, int nbk, double* Lout, int64_t ldl,
+                                               double* inv_out, int32_t* info, int info_base, int do_factor, int write_l,
+                                               double* s_vec /* [2][NB] + 2 pivots */, double* s_rinv /* [NB] */) {
+  const int tid = threadIdx.x;
+  const int tx = tid & 31, ty = tid >> 5;
+  const int i0 = 4 * ty, k0 = 4 * tx;
+  const bool lower_tile = tx <= ty;
+  double c[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + a, k = k0 + b;
+      double v = (i == k) ? 1.0 : 0.0;
+      if (lower_tile && k <= i && i < nbk && k < nbk) v = Ain[static_cast<int64_t>(i) * lda + k];
+      c[a][b] = v;
+    }
+  int par = 0;
+  if (do_factor) {
+    // The pivot of column j+1 is final as soon as step j has updated the diagonal tile: its owner computes
+    // 1/sqrt one step ahead and publishes it, so sqrt/div are executed by ONE thread per column, not by 1024.
+    auto pivot = [&](double ajj, int j) -> double {   // returns L_jj, publishes 1/L_jj
+      double d, rd;
+      if (!(ajj > 0.0)) {
+        atomicCAS(info, 0, info_base + j + 1);
+        d = rd = nan("");
+      } else {
+        rd = rsqrt(ajj);
+        d = ajj * rd;
+        d = fma(0.5 * rd, fma(-d, d, ajj), d);          // one Newton step: d = sqrt(ajj) to < 1 ulp
+        rd = 1.0 / d;
+      }
+      s_vec[2 * NB + (j & 1)] = rd;
+      s_rinv[j] = rd;
+      return d;
+    };
+    if (tid == 0) c[0][0] = pivot(c[0][0], 0);
+    for (int j = 0; j < NB; ++j) {
+      const int jb = j >> 2, jc = j & 3;
+      if (tx == jb && lower_tile) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+          double v = c[a][0];
+          if (jc == 1) v = c[a][1];
+          if (jc == 2) v = c[a][2];
+          if (jc == 3) v = c[a][3];
+          s_vec[par * NB + i0 + a] = v;
+        }
+      }
+      __syncthreads();
+      const double* col = s_vec + par * NB;
+      const double rd = s_vec[2 * NB + (j & 1)];
+      if (i0 + 3 >= j && lower_tile) {         // tiles entirely above row j are finished
+        double li[4], lk[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) li[a] = col[i0 + a] * rd;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) lk[b] = col[k0 + b] * rd;
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int i = i0 + a, k = k0 + b;
+            if (k > j && k <= i) c[a][b] = fma(-li[a], lk[b], c[a][b]);
+            if (k == j && i > j) c[a][b] = li[a];     // scaled column j of L (the diagonal already holds L_jj)
+          }
+        const int jn = j + 1;
+        if (jn < NB && tx == ty && tx == (jn >> 2)) {
+          const int an = jn & 3;
+          double ann = c[0][0];
+          if (an == 1) ann = c[1][1];
+          if (an == 2) ann = c[2][2];
+          if (an == 3) ann = c[3][3];
+          const double dn = pivot(ann, jn);
+          if (an == 0) c[0][0] = dn;
+          if (an == 1) c[1][1] = dn;
+          if (an == 2) c[2][2] = dn;
+          if (an == 3) c[3][3] = dn;
+        }
+      }
+      par ^= 1;
+    }
+  } else if (tid < NB) {
+    s_rinv[tid] = 1.0 / ((tid < nbk) ? Ain[static_cast<int64_t>(tid) * lda + tid] : 1.0);
+  }
+  // ---- L: registers -> shared (for loop 2) and -> global
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + a, k = k0 + b;
+      const double v = (lower_tile && k <= i) ? c[a][b] : 0.0;
+      W[i * LDSM + k] = v;
+      if (write_l && i < nbk && k < nbk) Lout[static_cast<int64_t>(i) * ldl + k] = v;
+      c[a][b] = (i == k) ? 1.0 : 0.0;          // becomes the X tile
+    }
+  __syncthreads();
+  // ---- loop 2: X = L^{-1}
+  for (int j = 0; j < NB; ++j) {
+    const int jb = j >> 2, ja = j & 3;
+    if (ty == jb && lower_tile) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        double v = c[0][b];
+        if (ja == 1) v = c[1][b];
+        if (ja == 2) v = c[2][b];
+        if (ja == 3) v = c[3][b];
+        s_vec[par * NB + k0 + b] = v;          // unscaled row j of X
+      }
+    }
+    __syncthreads();
+    const double* row = s_vec + par * NB;
+    const double rd = s_rinv[j];
+    if (i0 + 3 >= j && k0 <= j && lower_tile) {
+      double xj[4], lj[4];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) xj[b] = row[k0 + b] * rd;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) lj[a] = W[(i0 + a) * LDSM + j];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int i = i0 + a, t = k0 + b;
+          if (i > j && t <= j) c[a][b] = fma(-lj[a], xj[b], c[a][b]);
+          if (i == j && t <= j) c[a][b] = xj[b];      // scaled row j of X
+        }
+    }
+    par ^= 1;
+  }
+  if (inv_out) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int i = i0 + a, t = k0 + b;
+        inv_out[i * NB + t] = (lower_tile && t <= i) ? c[a][b] : 0.0;
+      }
+  }
+}
+
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* Ablk, int64_t lda, int nbk, double* inv_out, int32_t* info, int info_base, int do_factor,
                  int write_l) {
   extern __shared__ double W[];
-  const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;  // 32 x 32
-  __shared__ int s_bad;
-  if (tid == 0) s_bad = 0;
-
-  for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
-    const int i = e / NB, p = e - i * NB;
-    if (p <= i) {
-      double v = (i == p) ? 1.0 : 0.0;
-      if (i < nbk && p < nbk) v = Ablk[static_cast<int64_t>(i) * lda + p];
-      W[i * LDSM + p] = v;
-    } else {
-      // X^T region (t = i, column index p = i'+1): X starts as the identity; X[i'][t] with i' = p-1 >= t
-      W[i * LDSM + p] = (p - 1 == i) ? 1.0 : 0.0;
-    }
-  }
-  // last shifted column (p = NB) holds X[NB-1][t]
-  for (int t = tid; t < NB; t += POTF2_THREADS) W[t * LDSM + NB] = (t == NB - 1) ? 1.0 : 0.0;
-  __syncthreads();
-
-  for (int j = 0; j < NB; ++j) {
-    // ---- column j of L
-    if (do_factor) {
-      const double ajj = W[j * LDSM + j];
-      __syncthreads();  // everyone has read a_jj before it is overwritten
-      double d;
-      if (!(ajj > 0.0)) {
-        if (tid == 0 && s_bad == 0) { s_bad = 1; atomicCAS(info, 0, info_base + j + 1); }
-        d = nan("");
-      } else {
-        d = sqrt(ajj);
-      }
-      if (tid == 0) W[j * LDSM + j] = d;
-      const double rd = 1.0 / d;
-      for (int i = j + 1 + tid; i < NB; i += POTF2_THREADS) W[i * LDSM + j] = W[i * LDSM + j] * rd;
-      __syncthreads();
-    }
-    const double ljj = W[j * LDSM + j];
-    // ---- row j of X is final up to the division by L_jj:  X[j][t] /= L_jj, t <= j  (stored W[t][j+1])
-    for (int t = tid; t <= j; t += POTF2_THREADS) W[t * LDSM + j + 1] = W[t * LDSM + j + 1] / ljj;
-    __syncthreads();
-    // ---- trailing updates (both are rank-1):
-    //   A[i][k] -= L[i][j] * L[k][j]      j < k <= i          (only when factoring)
-    //   X[i][t] -= L[i][j] * X[j][t]      i > j, t <= j
-    if (do_factor) {
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = ty + 32 * a;
-        if (i <= j) continue;
-        const double lij = W[i * LDSM + j];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int k = tx + 32 * b;
-          if (k > j && k <= i) W[i * LDSM + k] -= lij * W[k * LDSM + j];
-        }
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int t = ty + 32 * b;
-      if (t > j) continue;
-      const double xjt = W[t * LDSM + j + 1];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = tx + 32 * a;
-        if (i > j) W[t * LDSM + i + 1] -= W[i * LDSM + j] * xjt;
-      }
-    }
-    __syncthreads();
-  }
-
-  // ---- write back: L (valid part, lower; strict upper of the block zeroed) and inv (full NB x NB, row-major)
-  for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
-    const int i = e / NB, p = e - i * NB;
-    if (write_l && i < nbk && p < nbk) Ablk[static_cast<int64_t>(i) * lda + p] = (p <= i) ? W[i * LDSM + p] : 0.0;
-    if (inv_out) inv_out[e] = (p <= i) ? W[p * LDSM + i + 1] : 0.0;
-  }
+  __shared__ double s_vec[2 * NB + 2];
+  __shared__ double s_rinv[NB];
+  block_chol_inv(W, Ablk, lda, nbk, Ablk, lda, inv_out, info, info_base, do_factor, write_l, s_vec, s_rinv);
 }
 
 bool g_potf2_attr[64] = {};
@@ -136,48 +207,14 @@ int launch_potf2_inv(double* Ablk, int64_t lda, int nbk, double* inv_out, int32_
 // batched trtri of the diagonal blocks of an existing L: one CTA per block
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 trtri_diag_kernel(const double* L, int64_t ldl, int n, double* invdiag) {
-  // thin wrapper: same algorithm as potf2_inv_kernel with do_factor = 0, one block per CTA
   extern __shared__ double W[];
+  __shared__ double s_vec[2 * NB + 2];
+  __shared__ double s_rinv[NB];
   const int blk = blockIdx.x;
   const int j0 = blk * NB;
   const int nbk = min(NB, n - j0);
-  const double* Ablk = L + static_cast<int64_t>(j0) * ldl + j0;
-  double* inv_out = invdiag + static_cast<int64_t>(blk) * NB * NB;
-  const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;
-  for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
-    const int i = e / NB, p = e - i * NB;
-    if (p <= i) {
-      double v = (i == p) ? 1.0 : 0.0;
-      if (i < nbk && p < nbk) v = Ablk[static_cast<int64_t>(i) * ldl + p];
-      W[i * LDSM + p] = v;
-    } else {
-      W[i * LDSM + p] = (p - 1 == i) ? 1.0 : 0.0;
-    }
-  }
-  for (int t = tid; t < NB; t += POTF2_THREADS) W[t * LDSM + NB] = (t == NB - 1) ? 1.0 : 0.0;
-  __syncthreads();
-  for (int j = 0; j < NB; ++j) {
-    const double ljj = W[j * LDSM + j];
-    for (int t = tid; t <= j; t += POTF2_THREADS) W[t * LDSM + j + 1] = W[t * LDSM + j + 1] / ljj;
-    __syncthreads();
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int t = ty + 32 * b;
-      if (t > j) continue;
-      const double xjt = W[t * LDSM + j + 1];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        const int i = tx + 32 * a;
-        if (i > j) W[t * LDSM + i + 1] -= W[i * LDSM + j] * xjt;
-      }
-    }
-    __syncthreads();
-  }
-  for (int e = tid; e < NB * NB; e += POTF2_THREADS) {
-    const int i = e / NB, p = e - i * NB;
-    inv_out[e] = (p <= i) ? W[p * LDSM + i + 1] : 0.0;
-  }
+  block_chol_inv(W, L + static_cast<int64_t>(j0) * ldl + j0, ldl, nbk, nullptr, 0,
+                 invdiag + static_cast<int64_t>(blk) * NB * NB, nullptr, 0, 0, 0, s_vec, s_rinv);
 }
 
 bool g_trtri_attr[64] = {};
