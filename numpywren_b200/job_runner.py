@@ -212,6 +212,11 @@ class TileEngine:
             return (buf.squeeze() if m.autosqueeze else buf), None, key, False
         self._wait_tile(key, stream)
         ref = m._get_block_ref(*idx) if hasattr(m, "_get_block_ref") else None
+        if ref is not None and key not in self.tile_event:
+            up = m._ready_event(*m.true_block_idx(*idx)) if hasattr(m, "_ready_event") else None
+            if up is not None:             # tile still arriving from the host on the upload stream
+                stream.wait_event(up)
+                ref.record_stream(stream)
         shifted = (len(set(idx)) == 1 and len(set(m.shape)) == 1 and len(m.shape) != 1 and m.lambdav != 0)
         if ref is None or shifted:
             # default tile (parent_fn), transposed view, or diagonal shift: the public path makes a private copy
@@ -298,6 +303,9 @@ class TileEngine:
             for (m, idx), tile in zip(node.writes, results):
                 self._store(m, idx, tile, stream, ev)
             ev.record(stream)
+            for (m, idx), tile in zip(node.writes, results):
+                if hasattr(m, "_after_put"):
+                    m._after_put(m.true_block_idx(*idx), m._get_block_ref(*idx), ev)   # write-through host mirror
             if self.profile:
                 t1 = torch.cuda.Event(enable_timing=True)
                 t1.record(stream)

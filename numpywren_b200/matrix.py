@@ -61,7 +61,9 @@ class _HbmObjectStore:
         self.buckets: Dict[str, Dict[str, Dict[str, Any]]] = {}
 
     def entry(self, bucket, key_base):
-        return self.buckets.setdefault(bucket, {}).setdefault(key_base, {"header": None, "blocks": {}})
+        # "ready": CUDA events of tiles still being uploaded asynchronously; "mirror": write-through host copies
+        return self.buckets.setdefault(bucket, {}).setdefault(
+            key_base, {"header": None, "blocks": {}, "ready": {}, "mirror": None, "mirror_events": {}})
 
     def drop(self, bucket, key_base):
         self.buckets.get(bucket, {}).pop(key_base, None)
@@ -76,6 +78,16 @@ class _HbmObjectStore:
 
 
 STORE = _HbmObjectStore()
+
+_COPY_STREAMS: Dict[int, Tuple["torch.cuda.Stream", "torch.cuda.Stream"]] = {}
+
+
+def copy_streams(device: torch.device):
+    """(upload, download) side streams of a device: host<->HBM tile traffic overlaps the compute streams."""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    if idx not in _COPY_STREAMS:
+        _COPY_STREAMS[idx] = (torch.cuda.Stream(device=device), torch.cuda.Stream(device=device))
+    return _COPY_STREAMS[idx]
 
 
 def _run_coro(coro):
@@ -271,6 +283,63 @@ class BigMatrix(object):
         """Adopt ``tile`` as the stored tensor (no copy).  Scheduler-internal."""
         self._blocks_store[tuple(int(i) for i in block_idx)] = tile
 
+    @property
+    def _entry(self):
+        return STORE.entry(self.bucket, self.key_base)
+
+    def _ready_event(self, *block_idx):
+        """Event of an asynchronous upload still in flight for this tile (None once nobody registered one)."""
+        return self._entry["ready"].get(tuple(int(i) for i in block_idx))
+
+    def _upload_async(self, host_tile: torch.Tensor, block_idx):
+        """Pinned host tile -> new HBM tile on the upload stream; consumers wait on the recorded event."""
+        up, _ = copy_streams(self.device)
+        with torch.cuda.stream(up):
+            tile = torch.empty(host_tile.shape, dtype=host_tile.dtype, device=self.device)
+            tile.copy_(host_tile, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(up)
+        self._blocks_store[block_idx] = tile
+        self._entry["ready"][block_idx] = ev
+
+    # ---- write-through host mirror (the analogue of "the PUT made the tile durable"): every tile stored into this
+    # matrix is also copied to pinned host memory on the download stream, overlapping the rest of the program.
+    def mirror_to_host(self, buffers=None):
+        """Enable the mirror.  ``buffers``: optional {block_idx: pinned CPU tensor}; missing ones are allocated."""
+        e = self._entry
+        e["mirror"] = dict(buffers) if buffers else {}
+        e["mirror_events"] = {}
+        return self
+
+    def _after_put(self, block_idx, tile, event=None):
+        e = self._entry
+        if e["mirror"] is None or tile is None or not tile.is_cuda:
+            return
+        block_idx = tuple(int(i) for i in block_idx)
+        host = e["mirror"].get(block_idx)
+        if host is None:
+            host = torch.empty(tile.shape, dtype=tile.dtype, pin_memory=True)
+            e["mirror"][block_idx] = host
+        _, down = copy_streams(tile.device)
+        if event is not None:
+            down.wait_event(event)
+        else:
+            down.wait_stream(torch.cuda.current_stream(tile.device))
+        with torch.cuda.stream(down):
+            host.view(tile.shape).copy_(tile, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(down)
+        tile.record_stream(down)
+        e["mirror_events"][block_idx] = ev
+
+    def wait_mirror(self):
+        """Block until every mirrored tile has landed in host memory; returns {block_idx: pinned tensor}."""
+        e = self._entry
+        for ev in e["mirror_events"].values():
+            ev.synchronize()
+        e["mirror_events"] = {}
+        return e["mirror"] or {}
+
     def get_block(self, *block_idx):
         """Tile at ``block_idx`` as a torch tensor on the owning device (reference matrix.py:266-310).
 
@@ -282,6 +351,10 @@ class BigMatrix(object):
             raise Exception("Get block query does not match shape {0} vs {1}".format(block_idx, self.shape))
         block_idx = tuple(int(i) for i in block_idx)
         stored = self._blocks_store.get(block_idx)
+        if stored is not None and stored.is_cuda:
+            ev = self._entry["ready"].get(block_idx)
+            if ev is not None:
+                torch.cuda.current_stream(stored.device).wait_event(ev)
         if stored is None and not self._is_local(block_idx):
             from . import parallel
             raise Exception("tile {0}{1} is owned by rank {2}; use numpy() (collective) or run it through a program".format(
@@ -324,7 +397,13 @@ class BigMatrix(object):
             raise Exception("{2} Incompatible block size: {0} vs {1}".format(shape, current_shape, self))
         if not self._is_local(block_idx):
             return None   # SPMD: every rank issues the same put, only the tile's owner stores it
-        self._blocks_store[block_idx] = self._to_tile(block)
+        if (isinstance(block, torch.Tensor) and not block.is_cuda and block.is_pinned() and block.is_contiguous()
+                and self.device.type == "cuda"):
+            self._upload_async(block.reshape(current_shape), block_idx)   # overlapped H2D, consumers wait on its event
+        else:
+            self._entry["ready"].pop(block_idx, None)
+            self._blocks_store[block_idx] = self._to_tile(block)
+        self._after_put(block_idx, self._blocks_store[block_idx])
         return None
 
     async def put_block_async(self, block, loop=None, *block_idx, no_overwrite=False):
@@ -335,14 +414,19 @@ class BigMatrix(object):
         return self.put_block(block, *block_idx)
 
     def delete_block(self, *block_idx):
-        self._blocks_store.pop(tuple(int(i) for i in block_idx), None)
+        block_idx = tuple(int(i) for i in block_idx)
+        self._blocks_store.pop(block_idx, None)
+        self._entry["ready"].pop(block_idx, None)
 
     async def delete_block_async(self, loop=None, *block_idx):
         return self.delete_block(*block_idx)
 
     def free(self):
         """Delete all allocated blocks while leaving the matrix metadata intact."""
-        self._blocks_store.clear()
+        e = self._entry
+        e["blocks"].clear()
+        e["ready"].clear()
+        e["mirror_events"] = {}
         return 0
 
     def delete(self):

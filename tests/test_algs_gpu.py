@@ -194,3 +194,27 @@ def test_tsqr_golden(golden_dir, unique_key, cuda_device, name):
             lvl, j = (int(x) for x in k.split("_")[1:])
             mat = {"R": Rs, "V": Vs, "Tq": Ts}[k.split("_")[0]]
             assert rel(mat.get_block(lvl, j).cpu().numpy(), g[k]) < TOL, k
+
+
+def test_async_upload_and_host_mirror(golden_dir, unique_key, cuda_device):
+    """The end-to-end path bench.py times: pinned host tiles go in through put_block (asynchronous H2D, consumers wait on
+    the tile's event), factor tiles are written through to pinned host memory while the program is still running."""
+    g = np.load(os.path.join(golden_dir, "cholesky_64_16.npz"))
+    n, b = 64, 16
+    A = BigMatrix(unique_key("e2e"), shape=(n, n), shard_sizes=(b, b))
+    for (j, k) in A.block_idxs:
+        h = torch.from_numpy(np.ascontiguousarray(g["A"][j * b:(j + 1) * b, k * b:(k + 1) * b])).pin_memory()
+        A.put_block(h, j, k)
+        assert A._ready_event(j, k) is not None
+    program, meta = cholesky(A)
+    O = meta["outputs"][0]
+    O.mirror_to_host()
+    run(program, consume_inputs=True)
+    host = O.wait_mirror()
+    assert sorted(host) == [(j, k) for j in range(4) for k in range(j + 1)]
+    L = np.zeros((n, n))
+    for (j, k), t in host.items():
+        assert t.is_pinned()
+        L[j * b:(j + 1) * b, k * b:(k + 1) * b] = t.numpy()
+    assert rel(L, g["L"]) < TOL
+    assert rel(O.numpy(), g["L"]) < TOL
