@@ -26,167 +26,240 @@ int launch_fill2d(double* A, int64_t lda, int64_t rows, int64_t cols, int mode, 
 namespace {
 
 constexpr int NB = NPW_DIAG_NB;  // 128
-constexpr int LDSM = NB + 1;     // padded row stride (doubles) of the shared block
-constexpr int POTF2_THREADS = 1024;
-constexpr int POTF2_SMEM = NB * LDSM * 8;
+// One CTA of 256 threads factors a 128x128 block AND inverts the factor.  The matrix lives in REGISTERS as 8x8 tiles:
+// thread t owns tile (tx, ty) = (t >> 4, t & 15): rows 8ty.., cols 8tx.. (lower tiles: tx <= ty), so the 16 tiles of a
+// block column sit in one half-warp and warps retire as the factorisation moves right.
+//
+// Cholesky, blocked by 8 columns (2 barriers per sub-panel s):
+//   A  the diagonal thread (s,s) factors its 8x8 tile in registers and inverts it (X_ss), publishes X_ss;
+//   B  the tiles below it (one half-warp) form L21 = A21 X_ss^T and publish the panel, transposed and padded so that
+//      the rank-8 update reads it with conflict-free LDS.128;
+//   C  every tile to the right applies the rank-8 update from the published panel (512 DFMA per thread, no shared RMW).
+// Inverse X = L^{-1} by block forward substitution (1 barrier per block row q): with L'[s][q] = X_ss L[s][q] (each tile
+// pre-multiplied once, in parallel) X[s][t] = -sum_{q<s} L'[s][q] X[q][t]; row block q of X is published, every tile
+// below accumulates, the tiles of row q+1 are complete after step q.
+// do_factor = 0: the block already holds L (batched trtri).  Blocks smaller than NB are padded with the identity.
+constexpr int TS = 8;                    // register tile edge
+constexpr int NT = NB / TS;              // 16 tiles per dimension
+constexpr int PADR = NB + 2 * NT;        // padded row index space: pad(r) = r + 2*(r>>3)
+constexpr int POTF2_THREADS = NT * NT;   // 256
+// shared memory (doubles): LT[NT][TS][PADR] | XD[NT][TS*TS] | XR[2][TS][PADR]
+constexpr int SM_LT = 0;
+constexpr int SM_XD = SM_LT + NT * TS * PADR;
+constexpr int SM_XR = SM_XD + NT * TS * TS;
+constexpr int SM_END = SM_XR + 2 * TS * PADR;
+constexpr int POTF2_SMEM = SM_END * 8;
 
-// One CTA of 1024 threads factors a 128x128 block AND inverts the factor, with the matrix held in REGISTERS:
-// thread (tx, ty) = (tid & 31, tid >> 5) owns the 4x4 tile rows 4ty..4ty+3, cols 4tx..4tx+3 (lower tiles: tx <= ty).
-// Right-looking, one __syncthreads per column:
-//   loop 1 (Cholesky): the owners of column j publish it (unscaled) in a double-buffered shared vector; every thread
-//           derives d = sqrt(a_jj), 1/d itself and applies the rank-1 update to its register tile (no shared RMW);
-//   loop 2 (inverse X = L^{-1}, forward substitution by rows): the owners of row j of X publish it; every thread
-//           updates X[i][t] -= L[i][j] * X[j][t] / L_jj in registers, reading column j of L from shared memory.
-// do_factor = 0: the block already holds L (batched trtri of an existing factor).  Blocks smaller than NB are
-// padded with the identity.  Shared: L as W[NB][NB+1] (132 KB) + two small vectors.
-__device__ __forceinline__ void block_chol_inv(double* W, const double* Ain, int64_t lda, int nbk, double* Lout, int64_t ldl,
-                                               double* inv_out, int32_t* info, int info_base, int do_factor, int write_l,
-                                               double* s_vec /* [2][NB] + 2 pivots */, double* s_rinv /* [NB] */) {
-  const int tid = threadIdx.x;
-  const int tx = tid & 31, ty = tid >> 5;
-  const int i0 = 4 * ty, k0 = 4 * tx;
-  const bool lower_tile = tx <= ty;
-  double c[4][4];
+__device__ __forceinline__ int padr(int r) { return r + 2 * (r >> 3); }
+
+// in-register Cholesky of the lower 8x8 tile c (if do_factor) and its inverse x (lower); returns false on a bad pivot
+__device__ __forceinline__ void factor8(double (&c)[TS][TS], double (&x)[TS][TS], int do_factor, int32_t* info, int base) {
+  double rdv[TS];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = i0 + a, k = k0 + b;
-      double v = (i == k) ? 1.0 : 0.0;
-      if (lower_tile && k <= i && i < nbk && k < nbk) v = Ain[static_cast<int64_t>(i) * lda + k];
-      c[a][b] = v;
-    }
-  int par = 0;
-  if (do_factor) {
-    // The pivot of column j+1 is final as soon as step j has updated the diagonal tile: its owner computes
-    // 1/sqrt one step ahead and publishes it, so sqrt/div are executed by ONE thread per column, not by 1024.
-    auto pivot = [&](double ajj, int j) -> double {   // returns L_jj, publishes 1/L_jj
+  for (int j = 0; j < TS; ++j) {
+    if (do_factor) {
+      const double ajj = c[j][j];
       double d, rd;
       if (!(ajj > 0.0)) {
-        atomicCAS(info, 0, info_base + j + 1);
+        atomicCAS(info, 0, base + j + 1);
         d = rd = nan("");
       } else {
         rd = rsqrt(ajj);
         d = ajj * rd;
-        d = fma(0.5 * rd, fma(-d, d, ajj), d);          // one Newton step: d = sqrt(ajj) to < 1 ulp
+        d = fma(0.5 * rd, fma(-d, d, ajj), d);       // Newton: sqrt(ajj) to < 1 ulp
         rd = 1.0 / d;
       }
-      s_vec[2 * NB + (j & 1)] = rd;
-      s_rinv[j] = rd;
-      return d;
-    };
-    if (tid == 0) c[0][0] = pivot(c[0][0], 0);
-    for (int j = 0; j < NB; ++j) {
-      const int jb = j >> 2, jc = j & 3;
-      if (tx == jb && lower_tile) {
+      c[j][j] = d;
+      rdv[j] = rd;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          double v = c[a][0];
-          if (jc == 1) v = c[a][1];
-          if (jc == 2) v = c[a][2];
-          if (jc == 3) v = c[a][3];
-          s_vec[par * NB + i0 + a] = v;
-        }
-      }
-      __syncthreads();
-      const double* col = s_vec + par * NB;
-      const double rd = s_vec[2 * NB + (j & 1)];
-      if (i0 + 3 >= j && lower_tile) {         // tiles entirely above row j are finished
-        double li[4], lk[4];
+      for (int a = j + 1; a < TS; ++a) c[a][j] *= rd;
 #pragma unroll
-        for (int a = 0; a < 4; ++a) li[a] = col[i0 + a] * rd;
+      for (int b = j + 1; b < TS; ++b)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) lk[b] = col[k0 + b] * rd;
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int i = i0 + a, k = k0 + b;
-            if (k > j && k <= i) c[a][b] = fma(-li[a], lk[b], c[a][b]);
-            if (k == j && i > j) c[a][b] = li[a];     // scaled column j of L (the diagonal already holds L_jj)
-          }
-        const int jn = j + 1;
-        if (jn < NB && tx == ty && tx == (jn >> 2)) {
-          const int an = jn & 3;
-          double ann = c[0][0];
-          if (an == 1) ann = c[1][1];
-          if (an == 2) ann = c[2][2];
-          if (an == 3) ann = c[3][3];
-          const double dn = pivot(ann, jn);
-          if (an == 0) c[0][0] = dn;
-          if (an == 1) c[1][1] = dn;
-          if (an == 2) c[2][2] = dn;
-          if (an == 3) c[3][3] = dn;
-        }
-      }
-      par ^= 1;
+        for (int a = b; a < TS; ++a) c[a][b] = fma(-c[a][j], c[b][j], c[a][b]);
+    } else {
+      rdv[j] = 1.0 / c[j][j];
     }
-  } else if (tid < NB) {
-    s_rinv[tid] = 1.0 / ((tid < nbk) ? Ain[static_cast<int64_t>(tid) * lda + tid] : 1.0);
   }
-  // ---- L: registers -> shared (for loop 2) and -> global
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int j = 0; j < TS; ++j) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = i0 + a, k = k0 + b;
-      const double v = (lower_tile && k <= i) ? c[a][b] : 0.0;
-      W[i * LDSM + k] = v;
-      if (write_l && i < nbk && k < nbk) Lout[static_cast<int64_t>(i) * ldl + k] = v;
-      c[a][b] = (i == k) ? 1.0 : 0.0;          // becomes the X tile
+    for (int i = 0; i < TS; ++i) x[i][j] = 0.0;
+    x[j][j] = rdv[j];
+#pragma unroll
+    for (int i = j + 1; i < TS; ++i) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = j; q < i; ++q) s = fma(c[i][q], x[q][j], s);
+      x[i][j] = -rdv[i] * s;
     }
-  __syncthreads();
-  // ---- loop 2: X = L^{-1}
-  for (int j = 0; j < NB; ++j) {
-    const int jb = j >> 2, ja = j & 3;
-    if (ty == jb && lower_tile) {
+  }
+}
+
+__device__ __forceinline__ void block_chol_inv(double* sm, const double* Ain, int64_t lda, int nbk, double* Lout, int64_t ldl,
+                                               double* inv_out, int32_t* info, int info_base, int do_factor, int write_l) {
+  const int t = threadIdx.x;
+  const int tx = t >> 4, ty = t & 15;
+  const int r0 = TS * ty, c0 = TS * tx;
+  const bool lower = tx <= ty;
+  double* LT = sm + SM_LT;
+  double* XD = sm + SM_XD;
+  double* XR = sm + SM_XR;
+  double c[TS][TS];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        double v = c[0][b];
-        if (ja == 1) v = c[1][b];
-        if (ja == 2) v = c[2][b];
-        if (ja == 3) v = c[3][b];
-        s_vec[par * NB + k0 + b] = v;          // unscaled row j of X
-      }
+  for (int a = 0; a < TS; ++a)
+#pragma unroll
+    for (int b = 0; b < TS; ++b) {
+      const int i = r0 + a, k = c0 + b;
+      double v = (i == k) ? 1.0 : 0.0;
+      if (lower && k <= i && i < nbk && k < nbk) v = Ain[static_cast<int64_t>(i) * lda + k];
+      c[a][b] = v;
+    }
+
+  // ------------------------------------------------------------------ Cholesky (or, for trtri, just publish L)
+  for (int s = 0; s < NT; ++s) {
+    if (tx == s && ty == s) {                        // A: diagonal tile
+      double x[TS][TS];
+      factor8(c, x, do_factor, info, info_base + TS * s);
+#pragma unroll
+      for (int a = 0; a < TS; ++a)
+#pragma unroll
+        for (int b = 0; b < TS; ++b) XD[s * TS * TS + a * TS + b] = x[a][b];
     }
     __syncthreads();
-    const double* row = s_vec + par * NB;
-    const double rd = s_rinv[j];
-    if (i0 + 3 >= j && k0 <= j && lower_tile) {
-      double xj[4], lj[4];
+    if (tx == s && ty > s) {                         // B: panel below the diagonal tile
+      if (do_factor) {
+        const double* X = XD + s * TS * TS;          // L21 = A21 X^T : out[a][b] = sum_{q<=b} c[a][q] X[b][q]
 #pragma unroll
-      for (int b = 0; b < 4; ++b) xj[b] = row[k0 + b] * rd;
+        for (int b = TS - 1; b >= 0; --b) {
+          double xb[TS];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) lj[a] = W[(i0 + a) * LDSM + j];
+          for (int q = 0; q <= b; ++q) xb[q] = X[b * TS + q];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+          for (int a = 0; a < TS; ++a) {
+            double acc = 0.0;
 #pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          const int i = i0 + a, t = k0 + b;
-          if (i > j && t <= j) c[a][b] = fma(-lj[a], xj[b], c[a][b]);
-          if (i == j && t <= j) c[a][b] = xj[b];      // scaled row j of X
+            for (int q = 0; q <= b; ++q) acc = fma(c[a][q], xb[q], acc);
+            c[a][b] = acc;
+          }
         }
+      }
+      double* P = LT + s * TS * PADR + padr(r0);     // publish transposed: P[q][pad(row)]
+#pragma unroll
+      for (int q = 0; q < TS; ++q)
+#pragma unroll
+        for (int a = 0; a < TS; a += 2) *reinterpret_cast<double2*>(P + q * PADR + a) = make_double2(c[a][q], c[a + 1][q]);
     }
-    par ^= 1;
+    __syncthreads();
+    if (do_factor && tx > s && lower) {              // C: rank-8 update of everything to the right
+      const double* Pi = LT + s * TS * PADR + padr(r0);
+      const double* Pk = LT + s * TS * PADR + padr(c0);
+#pragma unroll
+      for (int q = 0; q < TS; ++q) {
+        double li[TS], lk[TS];
+#pragma unroll
+        for (int a = 0; a < TS; a += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(Pi + q * PADR + a);
+          li[a] = v.x; li[a + 1] = v.y;
+          const double2 w = *reinterpret_cast<const double2*>(Pk + q * PADR + a);
+          lk[a] = w.x; lk[a + 1] = w.y;
+        }
+#pragma unroll
+        for (int a = 0; a < TS; ++a)
+#pragma unroll
+          for (int b = 0; b < TS; ++b) c[a][b] = fma(-li[a], lk[b], c[a][b]);
+      }
+    }
   }
-  if (inv_out) {
+  // ---- L to global (lower; the strict upper of the block is zeroed)
+  if (write_l) {
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < TS; ++a)
 #pragma unroll
-      for (int b = 0; b < 4; ++b) {
-        const int i = i0 + a, t = k0 + b;
-        inv_out[i * NB + t] = (lower_tile && t <= i) ? c[a][b] : 0.0;
+      for (int b = 0; b < TS; ++b) {
+        const int i = r0 + a, k = c0 + b;
+        if (i < nbk && k < nbk) Lout[static_cast<int64_t>(i) * ldl + k] = (lower && k <= i) ? c[a][b] : 0.0;
       }
   }
+  if (!inv_out) return;
+  __syncthreads();
+  // ------------------------------------------------------------------ inverse
+  // L'[s][q] = X_ss L[s][q] for the off-diagonal tiles, re-published into LT; diagonal tiles become X_ss
+  if (lower && tx < ty) {
+    const double* X = XD + ty * TS * TS;             // X_ss of this tile's block row
+#pragma unroll
+    for (int a = TS - 1; a >= 0; --a) {              // new[a][b] = sum_{r<=a} X[a][r] c[r][b], rows bottom-up in place
+      double xa[TS];
+#pragma unroll
+      for (int r = 0; r <= a; ++r) xa[r] = X[a * TS + r];
+#pragma unroll
+      for (int b = 0; b < TS; ++b) {
+        double acc = 0.0;
+#pragma unroll
+        for (int r = 0; r <= a; ++r) acc = fma(xa[r], c[r][b], acc);
+        c[a][b] = acc;
+      }
+    }
+    double* P = LT + tx * TS * PADR + padr(r0);
+#pragma unroll
+    for (int q = 0; q < TS; ++q)
+#pragma unroll
+      for (int a = 0; a < TS; a += 2) *reinterpret_cast<double2*>(P + q * PADR + a) = make_double2(c[a][q], c[a + 1][q]);
+  }
+  // the tile registers now become X: diagonal tiles start as X_ss, the others accumulate from zero
+#pragma unroll
+  for (int a = 0; a < TS; ++a)
+#pragma unroll
+    for (int b = 0; b < TS; ++b) c[a][b] = (tx == ty) ? XD[ty * TS * TS + a * TS + b] : 0.0;
+  __syncthreads();
+  for (int q = 0; q < NT; ++q) {
+    double* XRq = XR + (q & 1) * TS * PADR;
+    if (ty == q && lower) {                          // publish row block q of X (final): XRq[row a][pad(col)]
+      // off-diagonal tiles hold +sum L' X: the sign of the substitution is applied here
+      const double sg = (tx == ty) ? 1.0 : -1.0;
+#pragma unroll
+      for (int a = 0; a < TS; ++a)
+#pragma unroll
+        for (int b = 0; b < TS; b += 2) {
+          c[a][b] *= sg; c[a][b + 1] *= sg;
+          *reinterpret_cast<double2*>(XRq + a * PADR + padr(c0) + b) = make_double2(c[a][b], c[a][b + 1]);
+        }
+    }
+    __syncthreads();
+    if (ty > q && tx <= q) {                         // acc[s][t] += L'[s][q] X[q][t]
+      const double* Pi = LT + q * TS * PADR + padr(r0);
+      const double* Xk = XRq + padr(c0);
+#pragma unroll
+      for (int r = 0; r < TS; ++r) {
+        double li[TS], xk[TS];
+#pragma unroll
+        for (int a = 0; a < TS; a += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(Pi + r * PADR + a);
+          li[a] = v.x; li[a + 1] = v.y;
+          const double2 w = *reinterpret_cast<const double2*>(Xk + r * PADR + a);
+          xk[a] = w.x; xk[a + 1] = w.y;
+        }
+#pragma unroll
+        for (int a = 0; a < TS; ++a)
+#pragma unroll
+          for (int b = 0; b < TS; ++b) c[a][b] = fma(li[a], xk[b], c[a][b]);
+      }
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < TS; ++a)
+#pragma unroll
+    for (int b = 0; b < TS; ++b) {
+      const int i = r0 + a, k = c0 + b;
+      inv_out[i * NB + k] = (lower && k <= i) ? c[a][b] : 0.0;
+    }
 }
 
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 potf2_inv_kernel(double* Ablk, int64_t lda, int nbk, double* inv_out, int32_t* info, int info_base, int do_factor,
                  int write_l) {
-  extern __shared__ double W[];
-  __shared__ double s_vec[2 * NB + 2];
-  __shared__ double s_rinv[NB];
-  block_chol_inv(W, Ablk, lda, nbk, Ablk, lda, inv_out, info, info_base, do_factor, write_l, s_vec, s_rinv);
+  extern __shared__ __align__(16) double sm[];
+  block_chol_inv(sm, Ablk, lda, nbk, Ablk, lda, inv_out, info, info_base, do_factor, write_l);
 }
 
 bool g_potf2_attr[64] = {};
@@ -207,14 +280,12 @@ int launch_potf2_inv(double* Ablk, int64_t lda, int nbk, double* inv_out, int32_
 // batched trtri of the diagonal blocks of an existing L: one CTA per block
 __global__ void __launch_bounds__(POTF2_THREADS, 1)
 trtri_diag_kernel(const double* L, int64_t ldl, int n, double* invdiag) {
-  extern __shared__ double W[];
-  __shared__ double s_vec[2 * NB + 2];
-  __shared__ double s_rinv[NB];
+  extern __shared__ __align__(16) double sm[];
   const int blk = blockIdx.x;
   const int j0 = blk * NB;
   const int nbk = min(NB, n - j0);
-  block_chol_inv(W, L + static_cast<int64_t>(j0) * ldl + j0, ldl, nbk, nullptr, 0,
-                 invdiag + static_cast<int64_t>(blk) * NB * NB, nullptr, 0, 0, 0, s_vec, s_rinv);
+  block_chol_inv(sm, L + static_cast<int64_t>(j0) * ldl + j0, ldl, nbk, nullptr, 0,
+                 invdiag + static_cast<int64_t>(blk) * NB * NB, nullptr, 0, 0, 0);
 }
 
 bool g_trtri_attr[64] = {};

@@ -284,6 +284,14 @@ def gemm(A, B, *args, **kwargs):
     return _gemm_into(out, None, A, B, ta, tb, 1.0, 0.0)
 
 
+def _gemm_accumulate(acc, A, B):
+    """acc += A @ B in place (the serial reduction loop of binops._gemm_remote_0, binops.py:19-33)."""
+    bm, ldb, b_t = _mat(B, "B")
+    if not b_t and min(acc.shape) >= 256:
+        return _gemm_into(acc, acc, A, transpose(B), False, True, 1.0, 1.0)
+    return _gemm_into(acc, acc, A, B, False, False, 1.0, 1.0)
+
+
 def _gemm_flops(A, B):
     m, n = A.shape
     k = B.shape[1]

@@ -218,3 +218,29 @@ def test_async_upload_and_host_mirror(golden_dir, unique_key, cuda_device):
         L[j * b:(j + 1) * b, k * b:(k + 1) * b] = t.numpy()
     assert rel(L, g["L"]) < TOL
     assert rel(O.numpy(), g["L"]) < TOL
+
+
+def test_binops_gemm(unique_key, cuda_device):
+    """tests/test_gemm.py:12-41 (legacy binops.gemm): single shard X X^T through a transposed view, and 2x2 shards X Y;
+    plus BASELINE config 1's shape class (tile 1024) against the oracle's restatement."""
+    from numpywren_b200 import binops
+    rs = np.random.RandomState(21)
+    X = rs.randn(16, 16)
+    Xs = BigMatrix(unique_key("bx"), shape=X.shape, shard_sizes=X.shape)
+    shard_matrix(Xs, X)
+    XXT = binops.gemm(None, Xs, Xs.T, Xs.bucket, 1)
+    assert np.all(np.isclose(X.dot(X.T), XXT.numpy()))
+    Y = rs.randn(16, 16)
+    Xh = BigMatrix(unique_key("bx2"), shape=X.shape, shard_sizes=(8, 8)); shard_matrix(Xh, X)
+    Yh = BigMatrix(unique_key("by2"), shape=Y.shape, shard_sizes=(8, 8)); shard_matrix(Yh, Y)
+    XY = binops.gemm(None, Xh, Yh, Xh.bucket, 1)
+    assert np.all(np.isclose(X.dot(Y), XY.numpy()))
+    n, b = 2048, 512
+    A, B = rs.randn(n, n), rs.randn(n, n)
+    Am = BigMatrix(unique_key("ba"), shape=(n, n), shard_sizes=(b, b)); shard_matrix(Am, A)
+    Bm = BigMatrix(unique_key("bb"), shape=(n, n), shard_sizes=(b, b)); shard_matrix(Bm, B)
+    oa = orc.OracleBigMatrix("a", (n, n), (b, b)); orc.shard_matrix(oa, A)
+    ob = orc.OracleBigMatrix("b", (n, n), (b, b)); orc.shard_matrix(ob, B)
+    assert rel(binops.gemm(None, Am, Bm).numpy(), orc.binops_gemm(oa, ob).numpy()) < TOL
+    with pytest.raises(Exception, match="shard size"):
+        binops.gemm(None, Xs, Yh)
