@@ -354,7 +354,7 @@ def _engine_for(program: lp.LambdaPackProgram, **opts) -> TileEngine:
         from . import parallel
         grid = parallel.current_grid()
         if grid is not None and grid.world > 1:
-            opts["comm"] = parallel.TileExchange(program.program, grid)
+            opts["comm"] = parallel.make_exchange(program.program, grid, torch.device("cuda", torch.cuda.current_device()))
         eng = TileEngine(program, **opts)
         program._engine = eng
         prio = eng.priorities()

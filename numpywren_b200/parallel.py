@@ -84,6 +84,9 @@ def init_from_env(backend: Optional[str] = None) -> ProcessGrid:
     if backend is None:
         backend = "nccl" if torch.cuda.is_available() else "gloo"
     if backend == "nccl":
+        # the engine uses ~6 compute streams plus one send and one receive stream per peer; give every stream its own
+        # hardware queue so that a signal wait at the head of one stream can never stall an unrelated one
+        os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
         torch.cuda.set_device(local)
     if world > 1 and not dist.is_initialized():
         # no device_id: with eager communicator init torch serialises unbatched P2P ops on the world
@@ -218,6 +221,118 @@ class TileExchange:
             work.wait()
         self.pending_sends = []
         self.cache.clear()
+
+
+_INBOX: Dict[str, Any] = {}
+
+
+def _symmetric_inbox(nbytes: int, device):
+    """A symmetric (peer-mapped) receive buffer shared by all programs of this process: allocated collectively once and
+    re-used while it is large enough.  Every rank must call this with the same size."""
+    import torch.distributed as dist
+    import torch.distributed._symmetric_memory as symm_mem
+    ent = _INBOX.get("inbox")
+    if ent is not None and ent[0] >= nbytes:
+        return ent[1], ent[2]
+    elems = (int(nbytes) + 7) // 8
+    buf = symm_mem.empty(elems, dtype=torch.float64, device=device)
+    hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+    _INBOX["inbox"] = (elems * 8, buf, hdl)
+    return buf, hdl
+
+
+class SymmTileExchange(TileExchange):
+    """Panel tiles are written straight into the consumer's HBM over NVLink (no NCCL, no SMs).
+
+    Every rank owns a symmetric *inbox* (torch symmetric memory: the same allocation is mapped into every peer's address
+    space).  The transfer plan gives each (tile, destination) a fixed slot in the destination's inbox, known to both
+    sides.  The producer enqueues, on a per-destination side stream: wait(producer event) → cudaMemcpyAsync of the tile
+    into the peer-mapped slot (copy engine) → put_signal(dst).  The consumer enqueues on a per-source side stream:
+    wait_signal(src) → record event; compute streams wait on that event and then read the tile *in place* from the inbox.
+    Signals are per (src, dst) binary semaphores consumed in plan order, so the k-th wait pairs with the k-th copy.
+    """
+
+    SIGNAL_TIMEOUT_MS = 120000
+
+    def __init__(self, compiled, grid: ProcessGrid, device):
+        super().__init__(compiled, grid)
+        self.device = device
+        # slot assignment in plan order (identical on every rank)
+        self.slot: Dict[Tuple[Any, int], int] = {}
+        counts = [0] * grid.world
+        slot_elems = 1
+        n_nodes = len(self.plan.exec_rank)
+        for nid in range(n_nodes):
+            for lst in (self.plan.before_node.get(nid, ()), self.plan.after_node.get(nid, ())):
+                for key, m, idx, src, dst in lst:
+                    self.slot[(key, dst)] = counts[dst]
+                    counts[dst] += 1
+                    slot_elems = max(slot_elems, int(np.prod(m.block_shape(*idx))))
+        self.slot_elems = (slot_elems + 15) // 16 * 16
+        self.max_slots = max(counts) if counts else 0
+        self.inbox, self.hdl = _symmetric_inbox(max(1, self.max_slots) * self.slot_elems * 8, device)
+        self.send_streams: Dict[int, torch.cuda.Stream] = {}
+        self.recv_streams: Dict[int, torch.cuda.Stream] = {}
+
+    def _stream(self, table, peer):
+        s = table.get(peer)
+        if s is None:
+            s = torch.cuda.Stream(device=self.device, priority=-1)
+            table[peer] = s
+        return s
+
+    def _do(self, transfers, engine, node_order_hint=None):
+        for key, m, idx, src, dst in transfers:
+            shape = tuple(m.block_shape(*idx))
+            off = self.slot[(key, dst)] * self.slot_elems
+            if src == self.rank:
+                ref = m._get_block_ref(*idx)
+                tile = m.get_block(*idx) if ref is None else ref
+                ev = engine.tile_event.get(key)
+                s = self._stream(self.send_streams, dst)
+                if ev is not None:
+                    s.wait_event(ev[0])
+                else:
+                    s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    peer = self.hdl.get_buffer(dst, shape, torch.float64, off)
+                    peer.copy_(tile.reshape(shape), non_blocking=True)
+                    self.hdl.put_signal(dst, 0, self.SIGNAL_TIMEOUT_MS)
+                tile.record_stream(s)
+                self.bytes_sent += tile.numel() * tile.element_size()
+            elif dst == self.rank:
+                r = self._stream(self.recv_streams, src)
+                with torch.cuda.stream(r):
+                    self.hdl.wait_signal(src, 0, self.SIGNAL_TIMEOUT_MS)
+                    ev = torch.cuda.Event()
+                    ev.record(r)
+                n = int(np.prod(shape))
+                buf = self.inbox[off:off + n].view(shape)
+                self.cache[key] = (buf, ev)
+                self.bytes_received += n * 8
+
+    def remote_tile(self, key, stream) -> Optional[torch.Tensor]:
+        ent = self.cache.get(key)
+        if ent is None:
+            return None
+        buf, ev = ent
+        stream.wait_event(ev)
+        return buf
+
+    def drain(self):
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        self.cache.clear()
+        # nobody may start overwriting inbox slots (next program) before every rank has finished reading them
+        dist.barrier(device_ids=[self.device.index])
+
+
+def make_exchange(compiled, grid: ProcessGrid, device):
+    """NVLink tile exchange for this program: peer-memory writes (default) or NCCL send/recv (NPW_B200_EXCHANGE=nccl)."""
+    mode = os.environ.get("NPW_B200_EXCHANGE", "symm")
+    if mode == "symm":
+        return SymmTileExchange(compiled, grid, device)
+    return TileExchange(compiled, grid)
 
 
 # ------------------------------------------------------------------------------------------- collectives on BigMatrix
