@@ -16,6 +16,22 @@ from .matrix import BigMatrix
 from .matrix_utils import constant_zeros
 
 
+def _place_by_row_block(mat, axis):
+    """Owner = (block index along ``axis``) mod world, expressed in the process grid's (row, col) coordinates."""
+    from . import parallel
+    if getattr(mat, "placement", None) is not None:
+        return
+
+    def placement(true_idx):
+        grid = parallel.current_grid()
+        j = int(true_idx[axis])
+        if grid is None:
+            return j, 0
+        r = j % grid.world
+        return r // grid.Q, r % grid.Q
+    mat.placement = placement
+
+
 def cholesky(X, truncate=0):
     """Tiled Cholesky of the SPD BigMatrix ``X`` → lower factor ``O`` (unwritten upper tiles read as zeros)."""
     b = X.shard_sizes[0]
@@ -47,6 +63,16 @@ def tsqr(X, truncate=0):
     V_sharded = BigMatrix("tsqr_V({0})".format(X.key), shape=(num_tree_levels * shard_size * b_fac, X.shape[0]),
                           shard_sizes=(shard_size * b_fac, shard_size), bucket=X.bucket, write_header=True, safe=False,
                           device=X.device)
+    # multi-GPU placement: everything derived from row block j lives on rank j mod world (leaves are embarrassingly
+    # parallel, only the R factors of the reduction tree cross GPUs); tile shapes are declared because these matrices
+    # are allocated with the reference's loose shapes (safe=False, alg_wrappers.py:36-38)
+    n = X.shape[1]
+    _place_by_row_block(X, axis=0)
+    for mat in (R_sharded, T_sharded, V_sharded):
+        _place_by_row_block(mat, axis=1)
+    R_sharded.tile_shape = lambda idx: (n, n)
+    T_sharded.tile_shape = lambda idx: (n, n)
+    V_sharded.tile_shape = lambda idx: (X.block_shape(idx[1], 0)[0], n) if idx[0] == 0 else (2 * n, n)
     t = time.time()
     p0 = lpcompile_for_execution(TSQR, inputs=["A"], outputs=["Rs"])
     p1 = p0(X, V_sharded, T_sharded, R_sharded, X.num_blocks(0))

@@ -54,6 +54,23 @@ def main():
     L = meta["outputs"][0].numpy()
     err = rel(L, np.linalg.cholesky(a))
     assert err < 1e-10, err
+    # TSQR: leaves live on rank j mod world, only R factors of the tree cross GPUs
+    from numpywren_b200.alg_wrappers import tsqr
+    g = np.load(os.path.join(ROOT, "tests", "golden", "tsqr_256_32.npz"))
+    X = BigMatrix("mg_tsqr", shape=(256, 32), shard_sizes=(32, 32))
+    program, meta = tsqr(X)              # placement is attached by the wrapper before tiles are stored
+    shard_matrix(X, g["X"])
+    assert sorted(X.block_idxs_exist) == [(j, 0) for j in range(8) if j % grid.world == grid.rank]
+    program.start()
+    job_runner.lambdapack_run(program, timeout=120)
+    assert program.program_status() == lp.PS.SUCCESS
+    Rs = meta["outputs"][0]
+    nlev = int(g["nlev"])
+    if grid.owner(Rs, (nlev, 0)) == grid.rank:
+        R = Rs.get_block(nlev, 0).cpu().numpy()
+        terr = rel(R, g["R"])
+        assert terr < 1e-10, terr
+        print(f"tsqr_256_32: world {grid.world} rel err {terr:.2e}")
     # a non-SPD matrix must fail on EVERY rank, whichever rank owns the offending tile
     bad = np.eye(64)
     bad[50, 50] = -1.0

@@ -55,6 +55,7 @@ def test_grid_shapes_and_ownership():
             return idx
     g = parallel.ProcessGrid(8, 3)
     assert g.owner(M(), (0, 0)) == 0 and g.owner(M(), (1, 0)) == 4 and g.owner(M(), (1, 3)) == 7
+    assert g.owner(M(), (0, 4)) == 4 and g.owner(M(), (1, 5)) == 1   # process row rotates every Q block columns
     assert g.owner(M(), (5, 2, 6)) == g.owner(M(), (2, 6))          # SSA version axis does not move a tile
     assert g.owner(M(), (3,)) == (3 % 2) * 4
     counts = [0] * 8
@@ -62,5 +63,11 @@ def test_grid_shapes_and_ownership():
         for k in range(j + 1):
             counts[g.owner(M(), (j, k))] += 1
     assert max(counts) - min(counts) <= 16 and min(counts) >= 56      # block-cyclic balances the lower triangle
+    # ... and the rotation balances the WORK (tile (j,k) receives k updates) to ~1 %
+    work = [0] * 8
+    for j in range(32):
+        for k in range(j + 1):
+            work[g.owner(M(), (j, k))] += k + 1
+    assert max(work) / (sum(work) / 8) < 1.03
     with pytest.raises(ValueError):
         parallel.ProcessGrid(8, 0, shape=(3, 3))
