@@ -48,7 +48,13 @@ struct PanelArgs {
 // scratch layout per parity buffer: [cta][32] partial sums, then [32] pivot row, starting at parity * SCR_STRIDE
 constexpr int SCR_STRIDE = MAX_GRID * QW + QW;
 
+// SMEM = true: the CTA's row chunk of the panel (<= QR_SMEM_ROWS rows x 32 columns) is loaded into shared memory once,
+// all 32 column passes run there, and the chunk is written back once (2 global passes instead of 64).
+constexpr int QR_SMEM_ROWS = 768;                    // 768 x 32 x 8 B = 192 KB
+
+template <bool SMEM>
 __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
+  extern __shared__ __align__(16) double s_chunk[];
   cg::grid_group grid = cg::this_grid();
   const int G = gridDim.x;
   const int cta = blockIdx.x;
@@ -71,12 +77,21 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
 
   for (int e = threadIdx.x; e < QW * (QW + 1); e += QTHREADS) (&s_T[0][0])[e] = 0.0;
 
+  auto rowptr = [&](int r) -> double* {
+    return SMEM ? s_chunk + static_cast<size_t>(r - r_lo) * QW : Vp + static_cast<int64_t>(r) * p.ldv;
+  };
+  if (SMEM) {
+    for (int r = r_lo + warp; r < r_hi; r += QWARPS)
+      s_chunk[static_cast<size_t>(r - r_lo) * QW + lane] = lane_ok ? Vp[static_cast<int64_t>(r) * p.ldv + lane] : 0.0;
+    __syncthreads();
+  }
+
   // ---- initial partials for column 0: g[c] = sum_{r > j0} x_r * P[r][c], x = column 0
   {
     double acc = 0.0;
     for (int r = r_lo + warp; r < r_hi; r += QWARPS) {
       if (r <= p.j0) continue;
-      const double v = lane_ok ? Vp[static_cast<int64_t>(r) * p.ldv + lane] : 0.0;
+      const double v = lane_ok ? rowptr(r)[lane] : 0.0;
       const double x = __shfl_sync(0xffffffffu, v, 0);
       acc = fma(x, v, acc);
     }
@@ -87,7 +102,7 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
       for (int q = 0; q < QWARPS; ++q) s += s_part[q][lane];
       p.scratch[cta * QW + lane] = s;
       if (p.j0 >= r_lo && p.j0 < r_hi)
-        p.scratch[MAX_GRID * QW + lane] = lane_ok ? Vp[static_cast<int64_t>(p.j0) * p.ldv + lane] : 0.0;
+        p.scratch[MAX_GRID * QW + lane] = lane_ok ? rowptr(p.j0)[lane] : 0.0;
     }
   }
 
@@ -137,7 +152,7 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
     double acc = 0.0;   // lane c > j: sum_{r > gj+1} x'_r P'[r][c] (x' = updated column j+1); lane i < j: sum v_i[r] v_j[r]
     const int rs = max(r_lo, gj);
     for (int r = rs + warp; r < r_hi; r += QWARPS) {
-      double* rowp = Vp + static_cast<int64_t>(r) * p.ldv;
+      double* rowp = rowptr(r);
       double v = lane_ok ? rowp[lane] : 0.0;
       if (r == gj) {
         // pivot row: v_j[gj] = 1; R(gj, c) = P[gj][c] - tau * w_c; diagonal becomes beta
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
       out[cta * QW + lane] = s;
       const int gn = gj + 1;                          // next pivot row
       if (j + 1 < w && gn >= r_lo && gn < r_hi && gn < p.m)
-        out[MAX_GRID * QW + lane] = lane_ok ? Vp[static_cast<int64_t>(gn) * p.ldv + lane] : 0.0;
+        out[MAX_GRID * QW + lane] = lane_ok ? rowptr(gn)[lane] : 0.0;
     }
     // ---- the Gram vector z_i = V[:,i]^T v_{j-1} (i < j-1) reduced this round belongs to column j-1 of T
     if (j > 0 && cta == 0 && threadIdx.x == 0) {
@@ -221,6 +236,11 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
       p.T[static_cast<int64_t>(p.j0 + i) * p.ldt + p.j0 + c] = (c >= i) ? s_T[i][c] : 0.0;
     }
     for (int e = threadIdx.x; e < w; e += QTHREADS) p.tau[p.j0 + e] = s_tau[e];
+  }
+  if (SMEM) {                                        // write the factored chunk back (V below the diagonal, explicit unit/zeros)
+    __syncthreads();
+    for (int r = r_lo + warp; r < r_hi; r += QWARPS)
+      if (lane_ok) Vp[static_cast<int64_t>(r) * p.ldv + lane] = s_chunk[static_cast<size_t>(r - r_lo) * QW + lane];
   }
 }
 
@@ -387,7 +407,9 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
       set_error("device does not support cooperative launch");
       return NPW_ERR_UNSUPPORTED;
     }
-    NPW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_panel_kernel, QTHREADS, 0));
+    NPW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_panel_kernel<false>, QTHREADS, 0));
+    NPW_CUDA_CHECK(cudaFuncSetAttribute(qr_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        QR_SMEM_ROWS * QW * static_cast<int>(sizeof(double))));
     int g = sms * (per_sm > 0 ? 1 : 0);
     if (g > MAX_GRID) g = MAX_GRID;
     if (g < 1) g = 1;
@@ -415,7 +437,13 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
     if (g > max_grid) g = max_grid;
     if (g < 1) g = 1;
     void* kargs[] = {&pa};
-    NPW_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(qr_panel_kernel), dim3(g), dim3(QTHREADS), kargs, 0, st));
+    const int64_t per = (rows + g - 1) / g;                 // rows per CTA, as the kernel computes it
+    if (per <= QR_SMEM_ROWS) {
+      NPW_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(qr_panel_kernel<true>), dim3(g), dim3(QTHREADS), kargs,
+                                                 static_cast<size_t>(per) * QW * sizeof(double), st));
+    } else {
+      NPW_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(qr_panel_kernel<false>), dim3(g), dim3(QTHREADS), kargs, 0, st));
+    }
     count_launch();
     const int64_t nt = n - j0 - w;                          // trailing columns
     if (nt > 0) {
