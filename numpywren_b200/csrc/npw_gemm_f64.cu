@@ -27,10 +27,10 @@ constexpr int BM = 128, BN = 128, BK = 16;
 constexpr int MMA_WARPS = 8;
 // 2 MMA warpgroups + 1 producer warpgroup (only its first lane issues TMA).  Register
 // allocation is per warpgroup: the kernel is compiled for 168 regs/thread (65536 / 384) and
-// rebalanced at run time with setmaxnreg: producer 40, MMA warps 232.
+// rebalanced at run time with setmaxnreg: producer 24, MMA warps 240.
 constexpr int NTHREADS = (MMA_WARPS + 4) * 32;
-constexpr int REGS_PRODUCER = 40;
-constexpr int REGS_MMA = 232;
+constexpr int REGS_PRODUCER = 24;
+constexpr int REGS_MMA = 240;
 constexpr int STAGES = 6;
 constexpr int STAGE_A = BM * BK * 8;
 constexpr int STAGE_B = BN * BK * 8;
@@ -131,29 +131,48 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const uint32_t b_off = STAGE_A + (wn * 32 + g) * 128;
   const uint32_t sw[2] = {static_cast<uint32_t>(((2 * c) ^ g) << 4), static_cast<uint32_t>(((2 * c + 1) ^ g) << 4)};
 
+  // Software-pipelined across stage boundaries: the fragments of (stage it+1, h=0) are fetched — including the wait on
+  // that stage's full barrier — while the last 64 DMMAs of stage `it` are still being issued, so the tensor pipe does
+  // not drain at every k-block.
+  auto load_frag = [&](const uint8_t* st, int h, double2 (&a)[8], double2 (&b)[4]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2*>(st + a_off + i * 1024 + sw[h]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(st + b_off + j * 1024 + sw[h]);
+  };
+  double2 a0[8], b0[4], a1[8], b1[4];
+  if (kt > 0) {
+    mbar_wait(&full[0], 0);
+    load_frag(smem, 0, a0, b0);
+  }
   for (int it = 0; it < kt; ++it) {
     const int s = it % STAGES;
-    const uint32_t ph = (it / STAGES) & 1;
-    mbar_wait(&full[s], ph);
     const uint8_t* st = smem + s * STAGE_BYTES;
+    load_frag(st, 1, a1, b1);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      double2 a[8], b[4];
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = *reinterpret_cast<const double2*>(st + a_off + i * 1024 + sw[h]);
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a0[i].x, b0[j].x);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(st + b_off + j * 1024 + sw[h]);
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a0[i].y, b0[j].y);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].x, b[j].x);
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i].y, b[j].y);
-    }
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a1[i].x, b1[j].x);
+    // every fragment of stage s is in registers (the DMMAs above consumed them): hand the slot back to the producer
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);
+    if (it + 1 < kt) {
+      const int s2 = (it + 1) % STAGES;
+      mbar_wait(&full[s2], ((it + 1) / STAGES) & 1);
+      load_frag(smem + s2 * STAGE_BYTES, 0, a0, b0);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], a1[i].y, b1[j].y);
   }
 
   // ----------------------------------------------------------------- epilogue

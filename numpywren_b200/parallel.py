@@ -138,6 +138,20 @@ class TransferPlan:
                     self.before_node.setdefault(n.nid, []).append((key, m, tuple(idx), src, dst))
         self.num_transfers = len(seen)
 
+    def assign_inbox_slots(self):
+        """Fixed inbox slot of every transfer: {(tile_key, dst): slot}, slot size in elements, slots per inbox.
+        Computed from the plan alone, hence identical on every rank; slots of one destination never overlap."""
+        slot: Dict[Tuple[Any, int], int] = {}
+        counts = [0] * self.grid.world
+        slot_elems = 1
+        for nid in range(len(self.exec_rank)):
+            for lst in (self.before_node.get(nid, ()), self.after_node.get(nid, ())):
+                for key, m, idx, src, dst in lst:
+                    slot[(key, dst)] = counts[dst]
+                    counts[dst] += 1
+                    slot_elems = max(slot_elems, int(np.prod(_tile_shape(m, idx))))
+        return slot, (slot_elems + 15) // 16 * 16, (max(counts) if counts else 0)
+
     def describe(self, rank: int) -> List[Tuple[str, Any, int]]:
         """Ordered communication script of one rank: [("send"|"recv", tile_key, peer)] — used by the tests to check
         that every send has a matching recv in the same relative order."""
@@ -271,19 +285,7 @@ class SymmTileExchange(TileExchange):
     def __init__(self, compiled, grid: ProcessGrid, device):
         super().__init__(compiled, grid)
         self.device = device
-        # slot assignment in plan order (identical on every rank)
-        self.slot: Dict[Tuple[Any, int], int] = {}
-        counts = [0] * grid.world
-        slot_elems = 1
-        n_nodes = len(self.plan.exec_rank)
-        for nid in range(n_nodes):
-            for lst in (self.plan.before_node.get(nid, ()), self.plan.after_node.get(nid, ())):
-                for key, m, idx, src, dst in lst:
-                    self.slot[(key, dst)] = counts[dst]
-                    counts[dst] += 1
-                    slot_elems = max(slot_elems, int(np.prod(_tile_shape(m, idx))))
-        self.slot_elems = (slot_elems + 15) // 16 * 16
-        self.max_slots = max(counts) if counts else 0
+        self.slot, self.slot_elems, self.max_slots = self.plan.assign_inbox_slots()
         self.inbox, self.hdl = _symmetric_inbox(max(1, self.max_slots) * self.slot_elems * 8, device)
         self.send_streams: Dict[int, torch.cuda.Stream] = {}
         self.recv_streams: Dict[int, torch.cuda.Stream] = {}

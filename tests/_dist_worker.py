@@ -76,6 +76,16 @@ def main():
                 fan[k] = fan.get(k, 0) + 1
     assert max(fan.values()) <= world - 1
 
+    # inbox slots of the peer-memory exchange: same table on every rank, dense and collision-free per destination
+    slot, slot_elems, max_slots = plan.assign_inbox_slots()
+    tables = [None] * world
+    dist.all_gather_object(tables, sorted((repr(k), v) for k, v in slot.items()))
+    assert all(t == tables[0] for t in tables)
+    assert slot_elems >= 16 and slot_elems % 16 == 0 and len(slot) == plan.num_transfers
+    for d in range(world):
+        mine_slots = sorted(v for (k, dst), v in slot.items() if dst == d)
+        assert mine_slots == list(range(len(mine_slots))) and len(mine_slots) <= max_slots
+
     # ---- failure agreement helper
     assert parallel.allreduce_max_int(rank * 3, torch.device("cpu")) == (world - 1) * 3
     dist.barrier()
