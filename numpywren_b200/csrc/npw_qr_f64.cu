@@ -115,14 +115,24 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
     const double* scr = p.scratch + par * SCR_STRIDE;
     {
       double s = 0.0;
-      for (int q = warp; q < G; q += QWARPS) s += scr[q * QW + lane];
+      {
+        // all partial vectors are fetched with independent loads (fixed order of addition: deterministic result)
+        double v[4];
+        int q = warp;
+        for (; q + 3 * QWARPS < G; q += 4 * QWARPS) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = __ldcg(scr + (q + u * QWARPS) * QW + lane);
+          s += v[0]; s += v[1]; s += v[2]; s += v[3];
+        }
+        for (; q < G; q += QWARPS) s += __ldcg(scr + q * QW + lane);
+      }
       s_part[warp][lane] = s;
       __syncthreads();
       if (warp == 0) {
         double t = 0.0;
         for (int q = 0; q < QWARPS; ++q) t += s_part[q][lane];
         s_vec[lane] = t;
-        s_prow[lane] = scr[MAX_GRID * QW + lane];
+        s_prow[lane] = __ldcg(scr + MAX_GRID * QW + lane);
       }
       __syncthreads();
     }
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
   {
     const double* scr = p.scratch + (w & 1) * SCR_STRIDE;
     double s = 0.0;
-    for (int q = warp; q < G; q += QWARPS) s += scr[q * QW + lane];
+    for (int q = warp; q < G; q += QWARPS) s += __ldcg(scr + q * QW + lane);
     s_part[warp][lane] = s;
     __syncthreads();
     if (warp == 0) {
