@@ -64,10 +64,12 @@ __device__ __forceinline__ void factor8(double (&c)[TS][TS], double (&x)[TS][TS]
         atomicCAS(info, 0, base + j + 1);
         d = rd = nan("");
       } else {
+        // this chain runs on ONE thread and sits on the critical path of the whole tile factorisation: no fp64
+        // division (a ~30-instruction dependent sequence), only rsqrt plus two Newton corrections
         rd = rsqrt(ajj);
         d = ajj * rd;
-        d = fma(0.5 * rd, fma(-d, d, ajj), d);       // Newton: sqrt(ajj) to < 1 ulp
-        rd = 1.0 / d;
+        d = fma(0.5 * rd, fma(-d, d, ajj), d);       // sqrt(ajj) to < 1 ulp
+        rd = fma(rd, fma(-d, rd, 1.0), rd);          // 1/d to < 1 ulp
       }
       c[j][j] = d;
       rdv[j] = rd;

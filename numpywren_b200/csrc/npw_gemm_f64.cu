@@ -127,6 +127,17 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+  // warm L2 with this CTA's C0 tile (read only in the epilogue, ~0.5 ms from now): two 128-byte lines per row
+  if (p.beta != 0.0 && p.C0 != nullptr && c < 2) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = tile_m * BM + wm * 64 + g + i * 8;
+      const int col = tile_n * BN + wn * 32 + 16 * c;
+      if (row < p.m && col < p.n)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.C0 + static_cast<int64_t>(row) * p.ldc0 + col));
+    }
+  }
+
   const uint32_t a_off = (wm * 64 + g) * 128;
   const uint32_t b_off = STAGE_A + (wn * 32 + g) * 128;
   const uint32_t sw[2] = {static_cast<uint32_t>(((2 * c) ^ g) << 4), static_cast<uint32_t>(((2 * c + 1) ^ g) << 4)};
@@ -179,6 +190,38 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int row0 = tile_m * BM + wm * 64 + g;
   const int col0 = tile_n * BN + wn * 32 + 2 * c;
   const bool has_c0 = (p.beta != 0.0) && (p.C0 != nullptr);
+  const bool interior = p.vec_ok && (tile_m * BM + BM <= p.m) && (tile_n * BN + BN <= p.n);
+  if (interior) {
+    // Fast path (full tile, 16-byte aligned): C0 may alias C, which would make the compiler serialise every load
+    // behind the previous store; instead 16 independent 16-byte loads (4 row groups x 4 column groups) are put in
+    // flight before anything is stored (the fragment registers are free by now).
+#pragma unroll
+    for (int ib = 0; ib < 8; ib += 4) {
+      double2 sv[4][4];
+      if (has_c0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            sv[i][j] = *reinterpret_cast<const double2*>(p.C0 + static_cast<int64_t>(row0 + (ib + i) * 8) * p.ldc0 + col0 + j * 8);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          double2 o;
+          if (has_c0) {
+            o.x = fma(p.alpha, acc[ib + i][j][0], p.beta * sv[i][j].x);
+            o.y = fma(p.alpha, acc[ib + i][j][1], p.beta * sv[i][j].y);
+          } else {
+            o.x = p.alpha * acc[ib + i][j][0];
+            o.y = p.alpha * acc[ib + i][j][1];
+          }
+          *reinterpret_cast<double2*>(p.C + static_cast<int64_t>(row0 + (ib + i) * 8) * p.ldc + col0 + j * 8) = o;
+        }
+    }
+    return;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = row0 + i * 8;
