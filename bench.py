@@ -422,12 +422,15 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", dest="n", type=int, default=None, help="matrix size N (default 65536 on 1 GPU, 131072 on more)")
     ap.add_argument("--tile", type=int, default=4096)
-    ap.add_argument("--streams", type=int, default=4)
+    ap.add_argument("--streams", type=int, default=None,
+                    help="compute streams per GPU (default 4 on one GPU, 8 on several: fewer head-of-line stalls on remote tiles)")
     ap.add_argument("--cpu-n", dest="cpu_n", type=int, default=16384, help="bounded CPU sample size")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.n is None:
         args.n = 65536 if args.gpus == 1 else 131072
+    if args.streams is None:
+        args.streams = 4 if args.gpus == 1 else 8
     if args.impl == "reference":
         return run_reference_arm(args)
     return run_gpu_arm(args)
