@@ -377,7 +377,15 @@ def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, 
     with program._lock:
         program._runner_active += 1
     lambda_start = time.time()
-    n_streams = streams if streams is not None else int(os.environ.get("NPW_B200_STREAMS", max(1, min(8, pipeline_width))))
+    if streams is not None:
+        n_streams = streams
+    elif "NPW_B200_STREAMS" in os.environ:
+        n_streams = int(os.environ["NPW_B200_STREAMS"])
+    else:
+        from . import parallel
+        grid = parallel.current_grid()
+        # several GPUs: more streams, so that a task waiting for a panel tile from another GPU stalls fewer local ones
+        n_streams = 8 if (grid is not None and grid.world > 1) else max(1, min(8, pipeline_width))
     n_high = high_streams if high_streams is not None else int(os.environ.get("NPW_B200_HIGH_STREAMS", 2))
     if inplace is None:
         inplace = os.environ.get("NPW_B200_INPLACE", "1") != "0"
