@@ -1,7 +1,7 @@
 """Allocate outputs/intermediates, bind a LambdaPACK program, wrap it in a LambdaPackProgram.
 
 Same call forms and return values as reference numpywren/alg_wrappers.py: ``cholesky`` :16-27,
-``tsqr`` :30-47, ``gemm`` :49-65 → ``(program, {"outputs": [...], "intermediates": [...],
+``tsqr`` :30-47, ``gemm`` :49-65, ``qr`` :67-91, ``bdfac`` :94-118 → ``(program, {"outputs": [...], "intermediates": [...],
 "compile_time": seconds})``.
 """
 import time
@@ -10,10 +10,10 @@ import numpy as np
 
 from . import config as npw_config
 from . import lambdapack as lp
-from .algs import CHOLESKY, GEMM, TSQR
+from .algs import BDFAC, CHOLESKY, GEMM, QR, TSQR
 from .compiler import lpcompile_for_execution
 from .matrix import BigMatrix
-from .matrix_utils import constant_zeros
+from .matrix_utils import constant_zeros, constant_zeros_ext
 
 
 def _place_by_row_block(mat, axis):
@@ -101,3 +101,54 @@ def gemm(A, B):
     c_time = time.time() - t
     program = lp.LambdaPackProgram(p1, config=npw_config.default())
     return program, {"outputs": [C_sharded], "intermediates": [Temp], "compile_time": c_time}
+
+
+def _loose(key, X, shape, shard_sizes, parent_fn=None):
+    """Intermediate of the QR/BDFAC programs: over-allocated index space, shape checks off (safe=False)."""
+    return BigMatrix(key, shape=shape, shard_sizes=shard_sizes, bucket=X.bucket, write_header=True, parent_fn=parent_fn,
+                     safe=False, device=X.device)
+
+
+def qr(A):
+    """Tiled Householder QR of the square BigMatrix ``A`` (algs.QR): outputs [Rs, Vs, Ts]; block row i of R is
+    Rs[i, i, 0] (diagonal) and Rs[i, k, 0], k > i.  Matrix names and shapes as reference alg_wrappers.py:67-91."""
+    b_fac = 2
+    N = A.shape[0]
+    N_blocks = A.num_blocks(0)
+    shard_size = A.shard_sizes[0]
+    num_tree_levels = max(int(np.ceil(np.log2(A.num_blocks(0)) / np.log2(b_fac))), 1) + 1
+    Vs = _loose("Vs", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros)
+    Ts = _loose("Ts", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros)
+    Rs = _loose("Rs", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros)
+    Ss = _loose("Ss", A, (2 * N, 2 * N, 2 * N, num_tree_levels * shard_size), (shard_size, shard_size, 1, 1), constant_zeros)
+    t = time.time()
+    p0 = lpcompile_for_execution(QR, inputs=["I"], outputs=["Rs"])
+    p1 = p0(A, Vs, Ts, Rs, Ss, N_blocks, 0)
+    c_time = time.time() - t
+    program = lp.LambdaPackProgram(p1, config=npw_config.default())
+    return program, {"outputs": [Rs, Vs, Ts], "intermediates": [Ss], "compile_time": c_time}
+
+
+def bdfac(A, truncate=0):
+    """Reduction of the square BigMatrix ``A`` to block-bidiagonal form (algs.BDFAC): outputs [L_LQ, R_QR]; the
+    diagonal block of stage i is R_QR[i, top level, i], the super-diagonal block L_LQ[i, top level, i + 1]
+    (reference tests/test_alg_correctness.py:262-265).  Allocation as reference alg_wrappers.py:94-118."""
+    b_fac = 2
+    N = A.shape[0]
+    N_blocks = A.num_blocks(0)
+    shard_size = A.shard_sizes[0]
+    num_tree_levels = max(int(np.ceil(np.log2(A.num_blocks(0)) / np.log2(b_fac))), 1) + 1
+    V_QR = _loose("V_QR", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size))
+    T_QR = _loose("T_QR", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size))
+    R_QR = _loose("R_QR", A, (2 * N, num_tree_levels, 2 * N), (shard_size, 1, shard_size), constant_zeros)
+    S_QR = _loose("S_QR", A, (2 * N, num_tree_levels, 2 * N, 2 * N), (1, 1, shard_size, shard_size), constant_zeros)
+    V_LQ = _loose("V_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size))
+    T_LQ = _loose("T_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size))
+    L_LQ = _loose("L_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size), constant_zeros_ext)
+    S_LQ = _loose("S_LQ", A, (2 * N, num_tree_levels, 2 * N, 2 * N), (1, 1, shard_size, shard_size), constant_zeros_ext)
+    t = time.time()
+    p0 = lpcompile_for_execution(BDFAC, inputs=["I"], outputs=["R_QR", "L_LQ"])
+    p1 = p0(A, V_QR, T_QR, S_QR, R_QR, V_LQ, T_LQ, S_LQ, L_LQ, N_blocks, truncate)
+    c_time = time.time() - t
+    program = lp.LambdaPackProgram(p1, config=npw_config.default())
+    return program, {"outputs": [L_LQ, R_QR], "intermediates": [S_LQ, S_QR, T_QR, V_QR, V_LQ, T_LQ], "compile_time": c_time}

@@ -33,7 +33,7 @@ from . import kernels
 from . import lambdapack as lp
 from .compiler import ExpandedNode, _tile_key
 
-HIGH_PRIORITY_KERNELS = ("chol", "trsm", "qr_factor", "qr_factor_triangular")
+HIGH_PRIORITY_KERNELS = ("chol", "trsm", "qr_factor", "qr_factor_triangular", "lq_factor")
 
 
 class LRUCache(object):

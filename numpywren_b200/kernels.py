@@ -23,6 +23,7 @@ from . import _capi
 
 __all__ = [
     "add_matrices", "syrk", "chol", "trsm", "gemm", "mul", "identity", "qr_factor",
+    "qr_factor_triangular", "qr_leaf", "qr_trailing_update", "lq_factor", "lq_leaf", "lq_trailing_update",
     "chol_async", "trsm_with_inverse", "transpose", "add_diag", "fill_random",
 ]
 
@@ -314,6 +315,85 @@ def _qr_flops(*blocks):
 
 
 qr_factor.flops = _qr_flops
+
+
+def qr_factor_triangular(x0, x1, **kwargs):
+    """(V, T, R) of the QR of two stacked upper-triangular factors  — kernels.py:132-134 → fast_qr_triangular :107-124."""
+    from . import qr as _qr
+    return _qr.qr_factor_triangular(x0, x1, **kwargs)
+
+
+def lq_factor(*blocks, **kwargs):
+    """(V^T, T^T, L) of the LQ of hstack(blocks)  — kernels.py:145-150."""
+    from . import qr as _qr
+    return _qr.lq_factor(*blocks, **kwargs)
+
+
+lq_factor.flops = _qr_flops
+
+
+def qr_leaf(V, T, S0, *args, **kwargs):
+    """Apply a leaf reflector block to a trailing tile  — kernels.py:160-164 (see qr.py for the two semantics)."""
+    from . import qr as _qr
+    return _qr.qr_leaf(V, T, S0)
+
+
+def lq_leaf(V, T, S0, *args, **kwargs):
+    """S0 - S0 V^T T^T V  — kernels.py:154-157."""
+    from . import qr as _qr
+    return _qr.lq_leaf(V, T, S0)
+
+
+def _qr_leaf_flops(V, T, S0):
+    c0 = V.shape[0] * S0.shape[0] * S0.shape[1]
+    c1 = T.shape[0] * V.shape[0] * S0.shape[1]
+    c2 = V.shape[0] * T.shape[0] * T.shape[1]
+    return c0 + c1 + c2 + S0.shape[0] * S0.shape[1]
+
+
+qr_leaf.flops = _qr_leaf_flops
+lq_leaf.flops = _qr_leaf_flops
+
+
+def qr_trailing_update(V, T, S0, S1, *args, **kwargs):
+    """Apply a tree-merge reflector block to a pair of trailing tiles  — kernels.py:181-188."""
+    from . import qr as _qr
+    return _qr.qr_trailing_update(V, T, S0, S1)
+
+
+def lq_trailing_update(V, T, S0, S1=None, *args, **kwargs):
+    """Row-wise mirror of qr_trailing_update  — kernels.py:199-208."""
+    from . import qr as _qr
+    return _qr.lq_trailing_update(V, T, S0, S1)
+
+
+def _qr_trailing_flops(V, T, S0, S1):
+    M, N = V.shape
+    c0 = M * S1.shape[0] * S1.shape[1]
+    c1 = T.shape[0] * T.shape[1] * S0.shape[1]
+    return 2 * c1 + c0 + T.shape[0] * T.shape[1]
+
+
+qr_trailing_update.flops = _qr_trailing_flops
+lq_trailing_update.flops = _qr_trailing_flops
+
+
+def _gemm_any(out, c0, A, B, trans_a, trans_b, alpha, beta):
+    """out = alpha * op(A) @ op(B) + beta * c0 for any operand layout.  Large products are brought to the DMMA core's
+    NT form (both operands K-contiguous) by re-laying an operand out with the HBM-bound transpose kernel
+    (2 x tile bytes of traffic against 2mnk flops); small ones go straight to the generic kernel."""
+    m = A.shape[1] if trans_a else A.shape[0]
+    k = A.shape[0] if trans_a else A.shape[1]
+    n = B.shape[0] if trans_b else B.shape[1]
+    if min(m, n) >= 128 and k >= 64:
+        X = A.T if trans_a else A            # op(A), m x k
+        if _mat(X, "A")[2]:
+            X = transpose(X.T)               # row-major copy of op(A)
+        Y = B if trans_b else B.T            # op(B)^T, n x k
+        if _mat(Y, "B")[2]:
+            Y = transpose(Y.T)               # row-major copy of op(B)^T
+        return _gemm_into(out, c0, X, Y, False, True, alpha, beta)
+    return _gemm_into(out, c0, A, B, trans_a, trans_b, alpha, beta)
 
 
 # ----------------------------------------------------------------------------- helpers (not in the reference)

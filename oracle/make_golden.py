@@ -10,8 +10,10 @@ Shims: stub modules for boto3/botocore/aiobotocore/redis/
 installed, no network); np.product = np.prod for numpy >= 2; an in-memory dict behind
 BigMatrix.get_block_async / put_block_async that keeps the reference's parent_fn / autosqueeze /
 lambdav logic (matrix.py:294-309) and put-side reshape/safe logic (matrix.py:349-358).
-For TSQR only, kernels.fast_qr is replaced by a scipy.linalg.lapack.dgeqrt restatement because
-its f2py module (dgeqrt3) exists only in the authors' S3 bucket (kernels.py:22-40,86-89).
+For TSQR / QR / BDFAC, kernels.fast_qr and kernels.fast_qr_triangular are replaced by
+scipy.linalg.lapack.dgeqrt / dtpqrt stand-ins because their f2py modules (dgeqrt3, dtpqrt) exist only in the
+authors' S3 bucket (kernels.py:22-40,86-89,107-110); everything else (qr_leaf, qr_trailing_update, lq_*, the DSL
+programs, the compiler) is the reference's own code.
 """
 import asyncio
 import json
@@ -206,21 +208,7 @@ def golden_gemm(ref, n, b, seed, name, record_dag=False):
 
 def golden_tsqr(ref, m, b, seed, name, record_dag=False):
     """test_tsqr recipe (tests/test_alg_correctness.py:72-102) with the scipy dgeqrt stand-in for fast_qr."""
-    import scipy.linalg
-    kernels = ref["kernels"]
-
-    def fast_qr_scipy(x):  # kernels.py:86-105 with lapack.dgeqrt(nb=n) == dgeqrt3's single T
-        mm, nn = x.shape
-        k = min(mm, nn)
-        a, t, info = scipy.linalg.lapack.dgeqrt(nn, np.asfortranarray(x))
-        r = np.triu(a)
-        v = np.triu(a.T).T.copy()
-        v = v[:, :k]
-        v[np.diag_indices(min(v.shape[0], v.shape[1]))] = 1
-        r = r[:r.shape[1], :]
-        return v, np.triu(t), r
-
-    kernels.fast_qr = fast_qr_scipy
+    install_qr_standins(ref)
     BigMatrix = ref["matrix"].BigMatrix
     ref["STORE"].clear()
     np.random.seed(seed)
@@ -244,6 +232,131 @@ def golden_tsqr(ref, m, b, seed, name, record_dag=False):
     print(name, "nodes", nnodes, "starters", len(prog.starters), "terminators", prog.num_terminators, "| |R| - |R_np| |max",
           np.abs(np.abs(Rfin) - np.abs(Rnp)).max())
     return {"nnodes": nnodes, "num_terminators": int(prog.num_terminators), "num_starters": len(prog.starters), "dag": dag}
+
+
+def install_qr_standins(ref):
+    """scipy LAPACK stand-ins for the two f2py modules, following kernels.py:86-105 and :107-124 line by line."""
+    import scipy.linalg
+    kernels = ref["kernels"]
+
+    def fast_qr_scipy(x):
+        mm, nn = x.shape
+        k = min(mm, nn)
+        a, t, info = scipy.linalg.lapack.dgeqrt(nn, np.asfortranarray(x))
+        r = np.triu(a)
+        v = np.triu(a.T).T.copy()
+        v = v[:, :k]
+        v[np.diag_indices(min(v.shape[0], v.shape[1]))] = 1
+        r = r[:r.shape[1], :]
+        return v, np.triu(t), r
+
+    def fast_qr_triangular_scipy(x0, x1):
+        n = x0.shape[1]
+        nb = min(n, 32)                                   # kernels.py:118
+        a, b, tb, info = scipy.linalg.lapack.dtpqrt(x0.shape[0], nb, np.asfortranarray(x0), np.asfortranarray(x1))
+        t = np.zeros((n, n))                              # kernels.py:116: the caller's n x n zero array, LDT = n
+        for k0 in range(0, n, nb):                        # dtpqrt fills nb x nb upper-triangular blocks in rows 0..nb-1
+            w = min(nb, n - k0)
+            t[:w, k0:k0 + w] = np.triu(tb[:w, k0:k0 + w])
+        r = np.triu(a)                                    # kernels.py:119
+        v = np.triu(b.T).T.copy()                         # kernels.py:120
+        v[np.diag_indices(min(v.shape[0], v.shape[1]))] = 1
+        return v, t, r
+
+    kernels.fast_qr = fast_qr_scipy
+    kernels.fast_qr_triangular = fast_qr_triangular_scipy
+
+
+def _store_tiles(ref, mats):
+    out = {}
+    for name, m in mats.items():
+        for k, v in ref["STORE"].items():
+            if k[0] == m.key:
+                out[name + "_" + "_".join(str(i) for i in k[1])] = v
+    return out
+
+
+def golden_qr(ref, n, b, seed, name, record_dag=False):
+    """test_qr recipe (tests/test_alg_correctness.py:160-187) through alg_wrappers.qr's allocation (:67-91)."""
+    install_qr_standins(ref)
+    BigMatrix = ref["matrix"].BigMatrix
+    cz = ref["matrix_utils"].constant_zeros
+    ref["STORE"].clear()
+    X = np.random.RandomState(seed).randn(n, n)
+    I = BigMatrix(f"QRI_{name}", shape=(n, n), shard_sizes=(b, b), write_header=False)
+    for bi in I._block_idxs():
+        sl = tuple(slice(s, e) for s, e in I.__block_idx_to_real_idx__(bi))
+        ref["STORE"][(I.key, bi)] = X[sl].copy()
+    nb = I.num_blocks(0)
+    ntl = max(int(np.ceil(np.log2(nb) / np.log2(2))), 1) + 1
+    mk = lambda key, shape, ss: BigMatrix(f"{key}_{name}", shape=shape, shard_sizes=ss, write_header=False, parent_fn=cz, safe=False)
+    Vs = mk("Vs", (2 * n, 2 * n, ntl), (b, b, 1)); Ts = mk("Ts", (2 * n, 2 * n, ntl), (b, b, 1))
+    Rs = mk("Rs", (2 * n, 2 * n, ntl), (b, b, 1)); Ss = mk("Ss", (2 * n, 2 * n, 2 * n, ntl * b), (b, b, 1, 1))
+    p0 = ref["compiler"].lpcompile_for_execution(ref["algs"].QR, inputs=["I"], outputs=["Rs"])
+    prog = p0(I, Vs, Ts, Rs, Ss, nb, 0)
+    nnodes, dag = replay(ref, prog, record_dag)
+    tiles = _store_tiles(ref, {"Vs": Vs, "Ts": Ts, "Rs": Rs, "Ss": Ss})
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), X=X, n=n, b=b, nnodes=nnodes, **tiles)
+    print(name, "nodes", nnodes, "starters", len(prog.starters), "terminators", prog.num_terminators, "tiles", len(tiles))
+    return {"nnodes": nnodes, "num_terminators": int(prog.num_terminators), "num_starters": len(prog.starters), "dag": dag}
+
+
+def golden_bdfac(ref, n, b, seed, name, truncate=0, record_dag=False):
+    """test_bdfac recipe (tests/test_alg_correctness.py:216-275) through alg_wrappers.bdfac's allocation (:94-118)."""
+    install_qr_standins(ref)
+    BigMatrix = ref["matrix"].BigMatrix
+    cz = ref["matrix_utils"].constant_zeros
+    cze = ref["matrix_utils"].constant_zeros_ext
+    ref["STORE"].clear()
+    np.random.seed(seed)
+    X = np.random.randn(n, n)
+    I = BigMatrix(f"BDI_{name}", shape=(n, n), shard_sizes=(b, b), write_header=False)
+    for bi in I._block_idxs():
+        sl = tuple(slice(s, e) for s, e in I.__block_idx_to_real_idx__(bi))
+        ref["STORE"][(I.key, bi)] = X[sl].copy()
+    nb = I.num_blocks(0)
+    ntl = max(int(np.ceil(np.log2(nb) / np.log2(2))), 1) + 1
+    mk = lambda key, shape, ss, pf=None: BigMatrix(f"{key}_{name}", shape=shape, shard_sizes=ss, write_header=False, parent_fn=pf, safe=False)
+    m = {"V_QR": mk("V_QR", (2 * n, ntl, 2 * n), (1, 1, b)), "T_QR": mk("T_QR", (2 * n, ntl, 2 * n), (1, 1, b)),
+         "R_QR": mk("R_QR", (2 * n, ntl, 2 * n), (b, 1, b), cz), "S_QR": mk("S_QR", (2 * n, ntl, 2 * n, 2 * n), (1, 1, b, b), cz),
+         "V_LQ": mk("V_LQ", (2 * n, ntl, 2 * n), (1, 1, b)), "T_LQ": mk("T_LQ", (2 * n, ntl, 2 * n), (1, 1, b)),
+         "L_LQ": mk("L_LQ", (2 * n, ntl, 2 * n), (1, 1, b), cze), "S_LQ": mk("S_LQ", (2 * n, ntl, 2 * n, 2 * n), (1, 1, b, b), cze)}
+    p0 = ref["compiler"].lpcompile_for_execution(ref["algs"].BDFAC, inputs=["I"], outputs=["R_QR", "L_LQ"])
+    prog = p0(I, m["V_QR"], m["T_QR"], m["S_QR"], m["R_QR"], m["V_LQ"], m["T_LQ"], m["S_LQ"], m["L_LQ"], nb, truncate)
+    nnodes, dag = replay(ref, prog, record_dag)
+    tiles = _store_tiles(ref, m)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), X=X, n=n, b=b, truncate=truncate, nnodes=nnodes, **tiles)
+    print(name, "nodes", nnodes, "starters", len(prog.starters), "terminators", prog.num_terminators, "tiles", len(tiles))
+    return {"nnodes": nnodes, "num_terminators": int(prog.num_terminators), "num_starters": len(prog.starters), "dag": dag}
+
+
+def golden_qr_kernels(ref):
+    """Per-kernel vectors of the QR/LQ update kernels straight from reference kernels.py (with the two stand-ins)."""
+    install_qr_standins(ref)
+    k = ref["kernels"]
+    rs = np.random.RandomState(11)
+    out = {}
+    for tag, n in (("s", 12), ("l", 40)):            # l: n > 32 exercises dtpqrt's blocked T storage
+        r0 = np.triu(rs.randn(n, n)); r1 = np.triu(rs.randn(n, n))
+        v, t, r = k.qr_factor_triangular(r0, r1)
+        a = rs.randn(n, n); s0 = rs.randn(n, n + 4); s1 = rs.randn(n, n + 4)
+        vq, tq, rq = k.qr_factor(a)
+        vm, tm, rm = k.qr_factor(r0, r1)
+        s01, s11 = k.qr_trailing_update(vm, tm, s0, s1)
+        wide = rs.randn(n, 2 * n)
+        vl, tl, ll = k.lq_factor(wide[:, :n], wide[:, n:])
+        c0 = rs.randn(n, n); c1 = rs.randn(n, n)     # lq_trailing_update slices V by S0.shape[0]: square tiles only
+        l01, l11 = k.lq_trailing_update(vl, tl, c0, c1)
+        vl1, tl1, ll1 = k.lq_factor(a)
+        out.update({f"{tag}_r0": r0, f"{tag}_r1": r1, f"{tag}_tri_v": v, f"{tag}_tri_t": t, f"{tag}_tri_r": r, f"{tag}_a": a,
+                    f"{tag}_s0": s0, f"{tag}_s1": s1, f"{tag}_vq": vq, f"{tag}_tq": tq, f"{tag}_rq": rq,
+                    f"{tag}_leaf": k.qr_leaf(vq, tq, a), f"{tag}_vm": vm, f"{tag}_tm": tm, f"{tag}_rm": rm, f"{tag}_s01": s01,
+                    f"{tag}_s11": s11, f"{tag}_wide": wide, f"{tag}_vl": np.ascontiguousarray(vl), f"{tag}_tl": np.ascontiguousarray(tl),
+                    f"{tag}_ll": np.ascontiguousarray(ll), f"{tag}_c0": c0, f"{tag}_c1": c1, f"{tag}_l01": l01, f"{tag}_l11": l11,
+                    f"{tag}_vl1": np.ascontiguousarray(vl1), f"{tag}_tl1": np.ascontiguousarray(tl1),
+                    f"{tag}_lqleaf": k.lq_leaf(vl1, tl1, c0)})
+    np.savez_compressed(os.path.join(OUT, "qr_kernels.npz"), **out)
+    print("qr_kernels.npz written")
 
 
 def golden_kernels(ref):
@@ -309,6 +422,13 @@ def main():
     meta["gemm_32_16"] = golden_gemm(ref, 32, 16, 5, "gemm_32_16")
     meta["tsqr_256_32"] = golden_tsqr(ref, 256, 32, 1, "tsqr_256_32", record_dag=True)           # test_tsqr shape
     meta["tsqr_128_16"] = golden_tsqr(ref, 128, 16, 2, "tsqr_128_16")
+    golden_qr_kernels(ref)
+    meta["qr_28_7"] = golden_qr(ref, 28, 7, 3, "qr_28_7", record_dag=True)                       # test_qr shape
+    meta["qr_16_8"] = golden_qr(ref, 16, 8, 4, "qr_16_8")                                        # test_qr_lambda shape
+    meta["qr_24_8"] = golden_qr(ref, 24, 8, 5, "qr_24_8")                                        # odd tile count (3)
+    meta["bdfac_16_4"] = golden_bdfac(ref, 16, 4, 0, "bdfac_16_4", record_dag=True)              # test_bdfac shape
+    meta["bdfac_16_4_trunc2"] = golden_bdfac(ref, 16, 4, 0, "bdfac_16_4_trunc2", truncate=2)     # test_bdfac_truncated
+    meta["bdfac_15_5"] = golden_bdfac(ref, 15, 5, 1, "bdfac_15_5")                               # odd tile count (3)
     meta["structure"] = structure_counts(ref)
     with open(os.path.join(OUT, "structure.json"), "w") as f:
         json.dump(meta, f, indent=0, sort_keys=True)

@@ -16,7 +16,15 @@ exist in the authors' S3 bucket (kernels.py:22-40,86-89), so ``qr_factor`` here 
 kernels.py:86-105 with SciPy's LAPACK ``dgeqrt`` (nb = n gives the single n x n T that
 ``dgeqrt3`` returns).  For that kernel the oracle is pinned only against NumPy's QR
 (|R| equality, Q-orthogonality, the reference test's own criterion
-tests/test_alg_correctness.py:95-102): "parity unpinned" beyond that.
+tests/test_alg_correctness.py:95-102): "parity unpinned" beyond that.  The same holds for
+``fast_qr_triangular`` (f2py ``dtpqrt`` module → SciPy's LAPACK ``dtpqrt``).
+
+QR / BDFAC (``run_qr`` / ``run_bdfac``) exist in two semantics.  ``"reference"`` restates the code as written,
+including its work-in-progress placeholders (qr_leaf = ``S0 - V.T @ S0``, kernels.py:160-164; the triangular
+merge's V collapsing to the identity, kernels.py:120-122) and is pinned bit for bit against a replay of the
+unmodified reference programs (tests/golden/qr_*.npz, bdfac_*.npz).  ``"householder"`` is the intended algorithm,
+pinned by the criteria of the reference's own tests (tests/test_alg_correctness.py:160-187, 216-275): R equals
+np.linalg.qr's up to row signs; the block-bidiagonal factor has the singular values of the input.
 """
 from __future__ import annotations
 
@@ -97,6 +105,93 @@ def fast_qr(x):
 def qr_factor(*blocks):
     """kernels.py:127-130."""
     return fast_qr(np.vstack(blocks))
+
+
+def _blocked_triu(t, nb):
+    """Keep the upper triangle of every nb-wide column block of the nb x n array t (LAPACK's blocked T storage)."""
+    out = np.zeros_like(t)
+    n = t.shape[1]
+    for k0 in range(0, n, nb):
+        w = min(nb, n - k0)
+        out[:w, k0:k0 + w] = np.triu(t[:w, k0:k0 + w])
+    return out
+
+
+def fast_qr_triangular(x0, x1, semantics="reference"):
+    """kernels.py:107-124 with scipy's dtpqrt standing in for the f2py dtpqrt module (m = n, l = m, nb = min(n, 32)).
+
+    "reference": literal — ``v = np.triu(x1.T).T`` keeps the LOWER triangle of dtpqrt's upper-triangular V, so with the
+    unit diagonal v is the identity; t is the n x n zero array whose first nb rows hold LAPACK's blocked T.
+    "householder": v = dtpqrt's V2 (n x n upper triangular), t = the single n x n compact-WY T (nb = n),
+    Q = I - [I; V2] T [I; V2]^T.
+    """
+    m, n = x0.shape
+    if semantics == "householder":
+        a, b, t, info = scipy.linalg.lapack.dtpqrt(m, n, np.asfortranarray(x0), np.asfortranarray(x1))
+        if info != 0:
+            raise RuntimeError(f"dtpqrt info={info}")
+        return np.triu(b), np.triu(t), np.triu(a)
+    nb = min(n, 32)
+    a, b, t, info = scipy.linalg.lapack.dtpqrt(m, nb, np.asfortranarray(x0), np.asfortranarray(x1))
+    if info != 0:
+        raise RuntimeError(f"dtpqrt info={info}")
+    tfull = np.zeros((n, n))
+    tfull[:nb, :] = _blocked_triu(t, nb)
+    r = np.triu(a)
+    v = np.triu(b.T).T.copy()
+    v[np.diag_indices(min(v.shape[0], v.shape[1]))] = 1
+    return v, tfull, r
+
+
+def qr_factor_triangular(x0, x1, semantics="reference"):
+    """kernels.py:132-134."""
+    return fast_qr_triangular(x0, x1, semantics)
+
+
+def lq_factor(*blocks):
+    """kernels.py:145-150."""
+    if len(blocks) == 2:
+        assert blocks[0].shape[0] == blocks[1].shape[0]
+    ins = np.hstack(blocks)
+    v, t, r = fast_qr(ins.T)
+    return v.T, t.T, r.T
+
+
+def lq_leaf(V, T, S0):
+    """kernels.py:154-157."""
+    return S0 - S0 @ V.T @ T.T @ V
+
+
+def qr_leaf(V, T, S0, semantics="reference"):
+    """kernels.py:160-164: the code as written returns S0 - V.T @ S0 (the compact-WY line is commented out);
+    "householder" is that commented line, (I - V T V^T)^T S0."""
+    if semantics == "householder":
+        return S0 - (V @ (T.T @ (V.T @ S0)))
+    return S0 - (V.T @ S0)
+
+
+def qr_trailing_update(V, T, S0, S1, semantics="reference"):
+    """kernels.py:181-188."""
+    if S1 is None:
+        return qr_leaf(V, T, S0, semantics), np.zeros(S0.shape)
+    V = V[-S0.shape[0]:]
+    W = T.T @ (S0 + V.T @ S1)
+    S01 = S0 - W
+    S11 = S1 - V.dot(W)
+    return S01, S11
+
+
+def lq_trailing_update(V, T, S0, S1=None):
+    """kernels.py:199-208."""
+    if S1 is None:
+        return lq_leaf(V, T, S0), np.zeros(S0.shape)
+    V = V[:, -S0.shape[0]:]
+    W = (S0 + S1 @ V.T) @ T.T
+    S01 = S0 - W
+    S11 = S1 - W.dot(V)
+    assert S0.shape == S01.shape
+    assert S1.shape == S11.shape
+    return S01, S11
 
 
 def syrk_flops(s, x, y):
@@ -233,6 +328,11 @@ def constant_zeros(bigm, *block_idx):
     return np.zeros(tuple(e - s for s, e in real))
 
 
+def constant_zeros_ext(bigm, *block_idx):
+    """matrix_utils.py:319-325: always a shard x shard zero tile."""
+    return np.zeros((bigm.shard_sizes[-1], bigm.shard_sizes[-1]))
+
+
 def shard_matrix(bigm, X_local):
     """matrix_init.py:73-96: host ndarray → blocks."""
     for bidx, blk in zip(bigm.block_idxs, bigm.blocks):
@@ -321,6 +421,136 @@ def run_tsqr(A):
             v, t, r = qr_factor(Rs.get_block(level, j), Rs.get_block(level, j + 2 ** level))
             Vs.put_block(v, level + 1, j); Ts.put_block(t, level + 1, j); Rs.put_block(r, level + 1, j)
     return Rs, Vs, Ts
+
+
+def _ceil_log2(x):
+    """ceiling(log(x)/log(2)) for a positive integer x, exact (the DSL evaluates it with sympy)."""
+    return 0 if x <= 1 else (int(x) - 1).bit_length()
+
+
+def run_qr(A, semantics="reference"):
+    """algs.QR (algs.py:182-234) with alg_wrappers.qr's allocation (alg_wrappers.py:67-91).  Returns (Rs, Vs, Ts, S)."""
+    N = A.shape[0]
+    nb = A.num_blocks(0)
+    b = A.shard_sizes[0]
+    ntl = max(int(np.ceil(np.log2(nb) / np.log2(2))), 1) + 1
+    mk = lambda key, shape, ss: OracleBigMatrix(key, shape, ss, parent_fn=constant_zeros, safe=False)
+    Vs = mk("Vs", (2 * N, 2 * N, ntl), (b, b, 1))
+    Ts = mk("Ts", (2 * N, 2 * N, ntl), (b, b, 1))
+    Rs = mk("Rs", (2 * N, 2 * N, ntl), (b, b, 1))
+    S = mk("Ss", (2 * N, 2 * N, 2 * N, ntl * b), (b, b, 1, 1))
+    I = A
+    N = nb
+
+    def put3(res, idx):
+        Vs.put_block(res[0], *idx); Ts.put_block(res[1], *idx); Rs.put_block(res[2], *idx)
+
+    def panel(i, src, N_tree):
+        for j in range(i, N):
+            put3(qr_factor(src(j, i)), (j, i, N_tree))
+        for level in range(0, N_tree):
+            for j in range(i, N, 2 ** (level + 1)):
+                put3(qr_factor_triangular(Rs.get_block(j, i, N_tree - level), Rs.get_block(j + 2 ** level, i, N_tree - level),
+                                          semantics), (j, i, N_tree - level - 1))
+        for j in range(i, N):
+            for k in range(i + 1, N):
+                S.put_block(qr_leaf(Vs.get_block(j, i, N_tree), Ts.get_block(j, i, N_tree), src(j, k), semantics),
+                            j, k, i + 1, N_tree)
+        for k in range(i + 1, N):
+            for level in range(0, N_tree):
+                for j in range(i, N, 2 ** (level + 1)):
+                    s01, s11 = qr_trailing_update(Vs.get_block(j, i, N_tree - 1 - level), Ts.get_block(j, i, N_tree - 1 - level),
+                                                  S.get_block(j, k, i + 1, N_tree - level),
+                                                  S.get_block(j + 2 ** level, k, i + 1, N_tree - level), semantics)
+                    S.put_block(s01, j, k, i + 1, N_tree - 1 - level)
+                    S.put_block(s11, j + 2 ** level, k, i + 1, 0)
+        for k in range(i + 1, N):
+            Rs.put_block(identity(S.get_block(i, k, i + 1, 0)), i, k, 0)
+
+    panel(0, lambda j, k: I.get_block(j, k), _ceil_log2(N))
+    for i in range(1, N):
+        panel(i, lambda j, k, i=i: S.get_block(j, k, i, 0), _ceil_log2(N - i))
+    return Rs, Vs, Ts, S
+
+
+def run_bdfac(A, truncate=0, semantics="reference"):
+    """algs.BDFAC (algs.py:38-179) with alg_wrappers.bdfac's allocation (alg_wrappers.py:94-118).
+    Returns a dict of the eight matrices by their DSL names."""
+    NN = A.shape[0]
+    N = A.num_blocks(0)
+    b = A.shard_sizes[0]
+    ntl = max(int(np.ceil(np.log2(N) / np.log2(2))), 1) + 1
+    mk = lambda key, shape, ss, pf=None: OracleBigMatrix(key, shape, ss, parent_fn=pf, safe=False)
+    V_QR = mk("V_QR", (2 * NN, ntl, 2 * NN), (1, 1, b)); T_QR = mk("T_QR", (2 * NN, ntl, 2 * NN), (1, 1, b))
+    R_QR = mk("R_QR", (2 * NN, ntl, 2 * NN), (b, 1, b), constant_zeros)
+    S_QR = mk("S_QR", (2 * NN, ntl, 2 * NN, 2 * NN), (1, 1, b, b), constant_zeros)
+    V_LQ = mk("V_LQ", (2 * NN, ntl, 2 * NN), (1, 1, b)); T_LQ = mk("T_LQ", (2 * NN, ntl, 2 * NN), (1, 1, b))
+    L_LQ = mk("L_LQ", (2 * NN, ntl, 2 * NN), (1, 1, b), constant_zeros_ext)
+    S_LQ = mk("S_LQ", (2 * NN, ntl, 2 * NN, 2 * NN), (1, 1, b, b), constant_zeros_ext)
+    I = A
+
+    def qr_step(i, src, N_tree):
+        for j in range(i, N):
+            v, t, r = qr_factor(src(j, i))
+            V_QR.put_block(v, i, 0, j); T_QR.put_block(t, i, 0, j); R_QR.put_block(r, i, 0, j)
+            for k in range(i + 1, N):
+                S_QR.put_block(qr_leaf(V_QR.get_block(i, 0, j), T_QR.get_block(i, 0, j), src(j, k), semantics), i, 0, j, k)
+        for level in range(1, N_tree + 1):
+            for j in range(i, N, 2 ** level):
+                h = 2 ** (level - 1)
+                v, t, r = qr_factor(R_QR.get_block(i, level - 1, j), R_QR.get_block(i, level - 1, j + h))
+                V_QR.put_block(v, i, level, j); T_QR.put_block(t, i, level, j); R_QR.put_block(r, i, level, j)
+                for k in range(i + 1, N):
+                    s01, s11 = qr_trailing_update(V_QR.get_block(i, level, j), T_QR.get_block(i, level, j),
+                                                  S_QR.get_block(i, level - 1, j, k), S_QR.get_block(i, level - 1, j + h, k),
+                                                  semantics)
+                    S_QR.put_block(s01, i, level, j, k)
+                    S_QR.put_block(s11, i, N_tree, j + h, k)
+
+    def lq_step(i, N_tree_QR, N_tree_LQ):
+        for k in range(i + 1, N):
+            v, t, l = lq_factor(S_QR.get_block(i, N_tree_QR, i, k))
+            V_LQ.put_block(v, i, 0, k); T_LQ.put_block(t, i, 0, k); L_LQ.put_block(l, i, 0, k)
+            for j in range(i + 1, N):
+                S_LQ.put_block(lq_leaf(V_LQ.get_block(i, 0, k), T_LQ.get_block(i, 0, k), S_QR.get_block(i, N_tree_QR, j, k)),
+                               i, 0, j, k)
+        for level in range(1, N_tree_LQ + 1):
+            for k in range(i + 1, N, 2 ** level):
+                h = 2 ** (level - 1)
+                v, t, l = lq_factor(L_LQ.get_block(i, level - 1, k), L_LQ.get_block(i, level - 1, k + h))
+                V_LQ.put_block(v, i, level, k); T_LQ.put_block(t, i, level, k); L_LQ.put_block(l, i, level, k)
+                for j in range(i + 1, N):
+                    s01, s11 = lq_trailing_update(V_LQ.get_block(i, level, k), T_LQ.get_block(i, level, k),
+                                                  S_LQ.get_block(i, level - 1, j, k), S_LQ.get_block(i, level - 1, j, k + h))
+                    S_LQ.put_block(s01, i, level, j, k)
+                    S_LQ.put_block(s11, i, N_tree_LQ, j, k + h)
+
+    qr_step(0, lambda j, k: I.get_block(j, k), _ceil_log2(N))
+    lq_step(0, _ceil_log2(N), _ceil_log2(N - 1))
+    for i in range(1, N - 1 - truncate):
+        N_tree_QR = _ceil_log2(N - i)
+        prev_N_tree_LQ = _ceil_log2(N - i)
+        qr_step(i, lambda j, k, i=i, p=prev_N_tree_LQ: S_LQ.get_block(i - 1, p, j, k), N_tree_QR)
+        lq_step(i, N_tree_QR, _ceil_log2(N - i - 1))
+    # the last statement is a DAG node like any other: it runs once its input tile has been written, which a
+    # truncated program never does (the reference's node then simply never becomes ready)
+    if (N - 2, 0, N - 1, N - 1) in S_LQ.store:
+        v, t, r = qr_factor(S_LQ.get_block(N - 2, 0, N - 1, N - 1))
+        V_QR.put_block(v, N - 1, 0, N - 1); T_QR.put_block(t, N - 1, 0, N - 1); R_QR.put_block(r, N - 1, 0, N - 1)
+    return {"V_QR": V_QR, "T_QR": T_QR, "R_QR": R_QR, "S_QR": S_QR, "V_LQ": V_LQ, "T_LQ": T_LQ, "L_LQ": L_LQ, "S_LQ": S_LQ}
+
+
+def bdfac_assemble(R_QR, L_LQ, n, b, get=lambda m, *idx: m.get_block(*idx)):
+    """The block upper-bidiagonal factor from BDFAC's outputs, as the reference test assembles it
+    (tests/test_alg_correctness.py:262-265): diagonal block i = R_QR[i, top QR level of stage i, i], super-diagonal
+    block i = L_LQ[i, top LQ level of stage i, i + 1]."""
+    N = n // b
+    fac = np.zeros((n, n))
+    for i in range(N):
+        fac[i * b:(i + 1) * b, i * b:(i + 1) * b] = get(R_QR, i, _ceil_log2(N - i), i)
+        if i + 1 < N:
+            fac[i * b:(i + 1) * b, (i + 1) * b:(i + 2) * b] = get(L_LQ, i, _ceil_log2(N - i - 1), i + 1)
+    return fac
 
 
 def binops_gemm(X, Y):

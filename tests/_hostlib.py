@@ -1,0 +1,146 @@
+"""TEST DOUBLE for libnpw_b200's C-ABI on HOST memory (tests only — never imported by numpywren_b200/).
+
+The host side of the QR / LQ kernels (numpywren_b200/qr.py, kernels._gemm_any) is pure sequencing of C-ABI calls:
+which operand goes where, with which transpose flag, leading dimension, alpha/beta and aliasing.  That logic can be
+checked without a GPU by pointing the same Python code at an object that implements the handful of entry points it
+uses (include/npw_b200.h) with NumPy on raw host pointers.  ``install(monkeypatch)`` swaps it in for one test:
+CPU tensors are then accepted and every call is recorded in ``HostLib.calls``.  The real library is untouched, and
+on a GPU box the `-m gpu` tests exercise the very same Python code against the CUDA kernels.
+"""
+import ctypes
+
+import numpy as np
+import scipy.linalg
+
+
+def _view(ptr, rows, cols, ld):
+    if rows == 0 or cols == 0:
+        return np.zeros((rows, cols))
+    n = (rows - 1) * ld + cols
+    flat = np.ctypeslib.as_array(ctypes.cast(ctypes.c_void_p(int(ptr)), ctypes.POINTER(ctypes.c_double)), shape=(n,))
+    return np.lib.stride_tricks.as_strided(flat, shape=(rows, cols), strides=(ld * 8, 8))
+
+
+class HostLib:
+    def __init__(self):
+        self.calls = []
+
+    # -- bookkeeping entry points
+    def npw_last_error(self):
+        return b""
+
+    def npw_launch_count(self):
+        return len(self.calls)
+
+    def npw_geqrt_work_bytes(self, m, n):
+        return 8
+
+    # -- kernels (semantics: include/npw_b200.h)
+    def npw_gemm_f64(self, C, ldc, C0, ldc0, A, lda, transA, B, ldb, transB, m, n, k, alpha, beta, stream):
+        self.calls.append(("gemm", m, n, k, transA, transB))
+        a = _view(A, k, m, lda).T if transA else _view(A, m, k, lda)
+        b = _view(B, n, k, ldb).T if transB else _view(B, k, n, ldb)
+        acc = alpha * (a @ b)
+        if C0 and beta != 0.0:
+            acc = acc + beta * _view(C0, m, n, ldc0)
+        _view(C, m, n, ldc)[...] = acc
+        return 0
+
+    def npw_copy2d_f64(self, dst, ldd, src, lds, rows, cols, trans, stream):
+        self.calls.append(("copy2d", rows, cols, trans))
+        s = _view(src, rows, cols, lds)
+        if trans:
+            _view(dst, cols, rows, ldd)[...] = s.T
+        else:
+            _view(dst, rows, cols, ldd)[...] = s
+        return 0
+
+    def npw_fill2d_f64(self, A, lda, rows, cols, mode, value, stream):
+        self.calls.append(("fill2d", rows, cols, mode))
+        a = _view(A, rows, cols, lda)
+        i, j = np.indices((rows, cols))
+        if mode == 0:
+            a[...] = value
+        elif mode == 1:
+            a[j < i] = value
+        else:
+            a[j > i] = value
+        return 0
+
+    def npw_add_diag_f64(self, A, lda, rows, cols, lambdav, stream):
+        self.calls.append(("add_diag", rows, cols))
+        a = _view(A, rows, cols, lda)
+        d = np.arange(min(rows, cols))
+        a[d, d] += lambdav
+        return 0
+
+    def npw_addn_f64(self, out, ptrs, count, nelem, stream):
+        self.calls.append(("addn", count, nelem))
+        acc = np.zeros(nelem)
+        for c in range(count):
+            acc += _view(ptrs[c], 1, nelem, nelem)[0]
+        _view(out, 1, nelem, nelem)[0][...] = acc
+        return 0
+
+    def npw_geqrt_f64(self, V, ldv, T, ldt, R, ldr, A, lda, m, n, work, stream):
+        self.calls.append(("geqrt", m, n))
+        a = np.array(_view(A, m, n, lda))
+        qr, t, info = scipy.linalg.lapack.dgeqrt(n, np.asfortranarray(a))
+        assert info == 0
+        v = np.tril(qr, -1)[:, :n]
+        v[np.arange(n), np.arange(n)] = 1.0
+        _view(V, m, n, ldv)[...] = v
+        _view(T, n, n, ldt)[...] = np.triu(t)
+        _view(R, n, n, ldr)[...] = np.triu(qr)[:n]
+        return 0
+
+
+def install(monkeypatch):
+    """Route numpywren_b200's kernel wrappers to a HostLib and let them accept CPU tensors, for one test."""
+    import torch
+    from numpywren_b200 import _capi, kernels, qr
+    lib = HostLib()
+
+    def check_tile(t, name):
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{name}: expected a torch.Tensor")
+        if t.dtype != torch.float64:
+            raise TypeError(f"{name}: expected float64, got {t.dtype}")
+        if t.dim() != 2:
+            raise ValueError(f"{name}: expected a 2-D tile, got shape {tuple(t.shape)}")
+
+    monkeypatch.setattr(_capi, "load", lambda: lib)
+    for mod in (kernels, qr):
+        monkeypatch.setattr(mod, "_check_tile", check_tile)
+        monkeypatch.setattr(mod, "_stream", lambda: 0)
+    return lib
+
+
+def run_in_program_order(program):
+    """Execute every node of a compiled LambdaPACK program on host tiles, in source order (a valid schedule), through
+    the public BigMatrix.get_block/put_block and the node's bound kernel — the RemoteRead/RemoteCall/RemoteWrite triple
+    (reference lambdapack.py:225-384) without the GPU engine.  A node runs iff it is a starter or all of its (>= 1) DAG parents ran — the reference's readiness
+    rule (lambdapack.py:568-584); a node none of whose reads is ever written never becomes ready."""
+    import torch
+    compiled = program.program
+    starters = {(int(e), tuple(sorted((str(k), int(v)) for k, v in vv.items()))) for e, vv in compiled.starters}
+    done = set()
+    ran = 0
+    for node in compiled.nodes:
+        if node.key not in starters and not (node.parents and all(p in done for p in node.parents)):
+            continue
+        tiles = [m.get_block(*idx) for m, idx in node.reads]
+        args = []
+        for kind, j in node.arg_layout:
+            if kind == "read":
+                args.append(tiles[j])
+            elif isinstance(node.scalars[j], float):
+                args.append(node.scalars[j])
+        res = node.call.compute(*args)
+        res = res if isinstance(res, tuple) else (res,)
+        assert len(res) == len(node.writes)
+        for (m, idx), t in zip(node.writes, res):
+            m.put_block(t if isinstance(t, torch.Tensor) else torch.as_tensor(t), *idx)
+        done.add(node.nid)
+        ran += 1
+    return ran

@@ -80,6 +80,11 @@ def test_no_cpu_fallback():
         kernels.gemm(a, a)
     with pytest.raises(TypeError):
         kernels.syrk(np.zeros((4, 4)), a, a)
+    for fn, args in ((kernels.qr_factor, (a,)), (kernels.qr_factor_triangular, (a, a)), (kernels.lq_factor, (a,)),
+                     (kernels.qr_leaf, (a, a, a)), (kernels.lq_leaf, (a, a, a)), (kernels.qr_trailing_update, (a, a, a, a)),
+                     (kernels.lq_trailing_update, (a, a, a, a))):
+        with pytest.raises(_capi.NpwError, match="no CPU fallback"):
+            fn(*args)
 
 
 def test_flop_models_match_reference_formulas():

@@ -79,10 +79,19 @@ def test_gemm_and_tsqr_counts_match_reference(structure):
                 (ref["nodes"], ref["starters"], ref["terminators"]), name
 
 
-@pytest.mark.parametrize("which", ["cholesky_64_16", "gemm_64_16", "tsqr_256_32"])
+@pytest.mark.parametrize("which", ["cholesky_64_16", "gemm_64_16", "tsqr_256_32", "qr_28_7", "bdfac_16_4"])
 def test_dag_edges_equal_reference_symbolic_analysis(structure, which):
     dag = structure[which]["dag"]
-    if which.startswith("cholesky"):
+    if which.startswith("qr"):
+        p = compiler.lpcompile_for_execution(algs.QR, inputs=["I"], outputs=["Rs"])(
+            dummy_matrix(), dummy_matrix(3), dummy_matrix(3), dummy_matrix(3), dummy_matrix(4), 4, 0)
+        assert (len(p.starters), p.num_terminators) == (structure[which]["num_starters"], structure[which]["num_terminators"])
+    elif which.startswith("bdfac"):
+        p = compiler.lpcompile_for_execution(algs.BDFAC, inputs=["I"], outputs=["R_QR", "L_LQ"])(
+            dummy_matrix(), dummy_matrix(3), dummy_matrix(3), dummy_matrix(4), dummy_matrix(3), dummy_matrix(3), dummy_matrix(3),
+            dummy_matrix(4), dummy_matrix(3), 4, 0)
+        assert (len(p.starters), p.num_terminators) == (structure[which]["num_starters"], structure[which]["num_terminators"])
+    elif which.startswith("cholesky"):
         p = compiler.lpcompile(algs.CHOLESKY)(dummy_matrix(), dummy_matrix(), dummy_matrix(3), 4, 0)
     elif which.startswith("gemm"):
         p = compiler.lpcompile(algs.GEMM)(dummy_matrix(), dummy_matrix(), 4, 4, 4, dummy_matrix(4), dummy_matrix())

@@ -50,7 +50,8 @@ def native_trace(fn, arg_names, args):
 
     ns = {"ceiling": lambda x: int(math.ceil(round(x, 9))), "floor": lambda x: int(math.floor(round(x, 9))),
           "log": math.log, "BigMatrix": BigMatrix}
-    for k in ("chol", "trsm", "syrk", "gemm", "add_matrices", "identity", "qr_factor"):
+    for k in ("chol", "trsm", "syrk", "gemm", "add_matrices", "identity", "qr_factor", "qr_factor_triangular", "qr_leaf",
+              "qr_trailing_update", "lq_factor", "lq_leaf", "lq_trailing_update"):
         ns[k] = kernel(k)
     src = textwrap.dedent(inspect.getsource(fn))
     # tuple targets "A[..], B[..], C[..] = f(...)" assign the same call record to each target
@@ -77,6 +78,10 @@ CASES = [
     ("CHOLESKY", lambda n: (dummy(2), dummy(2), dummy(3), n, 2), [4, 7]),
     ("GEMM", lambda n: (dummy(2), dummy(2), n, n + 1, max(1, n - 1), dummy(4), dummy(2)), [1, 2, 3, 4, 5, 6, 17]),
     ("TSQR", lambda n: (dummy(2), dummy(2), dummy(2), dummy(2), n), [1, 2, 4, 8, 16, 32, 64]),
+    ("QR", lambda n: (dummy(2), dummy(3), dummy(3), dummy(3), dummy(4), n, 0), [1, 2, 3, 4, 5, 8, 11]),
+    ("BDFAC", lambda n: (dummy(2), dummy(3), dummy(3), dummy(4), dummy(3), dummy(3), dummy(3), dummy(4), dummy(3), n, 0),
+     [2, 3, 4, 5, 8, 9]),
+    ("BDFAC", lambda n: (dummy(2), dummy(3), dummy(3), dummy(4), dummy(3), dummy(3), dummy(3), dummy(4), dummy(3), n, 2), [4, 6]),
     ("SimpleTestLinear", lambda n: (dummy(2), dummy(2), n), [1, 3, 6]),
     ("SimpleTestLinear2", lambda n: (dummy(2), dummy(2), n), [2, 5]),
     ("SimpleTestNonLinear", lambda n: (dummy(3), dummy(1), n), [1, 2, 4, 8, 16]),

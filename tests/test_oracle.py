@@ -115,3 +115,101 @@ def test_spd_generator_is_well_conditioned():
     assert np.allclose(A, A.T)
     w = np.linalg.eigvalsh(A)
     assert w.min() > 0 and w.max() / w.min() < 10
+
+
+# --------------------------------------------------------------------------- QR / BDFAC
+def test_qr_update_kernels_match_reference(golden_dir):
+    g = _load(golden_dir, "qr_kernels.npz")
+    for tag in ("s", "l"):
+        v, t, r = orc.qr_factor_triangular(g[f"{tag}_r0"], g[f"{tag}_r1"])
+        assert np.array_equal(v, g[f"{tag}_tri_v"]) and np.array_equal(v, np.eye(v.shape[0]))   # kernels.py:120-122
+        assert np.array_equal(t, g[f"{tag}_tri_t"]) and np.array_equal(r, g[f"{tag}_tri_r"])
+        assert np.array_equal(orc.qr_leaf(g[f"{tag}_vq"], g[f"{tag}_tq"], g[f"{tag}_a"]), g[f"{tag}_leaf"])
+        s01, s11 = orc.qr_trailing_update(g[f"{tag}_vm"], g[f"{tag}_tm"], g[f"{tag}_s0"], g[f"{tag}_s1"])
+        assert np.array_equal(s01, g[f"{tag}_s01"]) and np.array_equal(s11, g[f"{tag}_s11"])
+        n = g[f"{tag}_a"].shape[0]
+        vl, tl, ll = orc.lq_factor(g[f"{tag}_wide"][:, :n], g[f"{tag}_wide"][:, n:])
+        assert np.array_equal(vl, g[f"{tag}_vl"]) and np.array_equal(tl, g[f"{tag}_tl"]) and np.array_equal(ll, g[f"{tag}_ll"])
+        l01, l11 = orc.lq_trailing_update(vl, tl, g[f"{tag}_c0"], g[f"{tag}_c1"])
+        assert np.array_equal(l01, g[f"{tag}_l01"]) and np.array_equal(l11, g[f"{tag}_l11"])
+        assert np.array_equal(orc.lq_leaf(g[f"{tag}_vl1"], g[f"{tag}_tl1"], g[f"{tag}_c0"]), g[f"{tag}_lqleaf"])
+
+
+def test_blocked_t_is_the_diagonal_of_the_compact_wy_t(golden_dir):
+    """dtpqrt (nb = 32 < n) stores the 32x32 diagonal blocks of the n x n compact-WY T side by side in rows 0..31 —
+    the identity numpywren_b200/qr.py uses to produce the reference's T from its own full T."""
+    g = _load(golden_dir, "qr_kernels.npz")
+    r0, r1 = g["l_r0"], g["l_r1"]
+    n = r0.shape[0]
+    _, t_ref, r_ref = orc.qr_factor_triangular(r0, r1)
+    v2, t_full, r_h = orc.qr_factor_triangular(r0, r1, semantics="householder")
+    assert not t_ref[32:].any()
+    for k0 in range(0, n, 32):
+        w = min(32, n - k0)
+        np.testing.assert_allclose(t_ref[:w, k0:k0 + w], t_full[k0:k0 + w, k0:k0 + w], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(r_h, r_ref, rtol=1e-12, atol=1e-14)
+    # the stacked general QR has the same reflectors: [I; V2], same T, same R
+    vs, ts, rs_ = orc.qr_factor(r0, r1)
+    np.testing.assert_allclose(vs[:n], np.eye(n), atol=0)
+    np.testing.assert_allclose(vs[n:], v2, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(ts, t_full, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(rs_, r_h, rtol=1e-11, atol=1e-13)
+
+
+def _check_tiles(g, mats):
+    n = 0
+    for k in g.files:
+        name = next((m for m in mats if k.startswith(m + "_")), None)
+        if name is None:
+            continue
+        idx = tuple(int(x) for x in k[len(name) + 1:].split("_"))
+        got = mats[name].store[idx]
+        assert got.shape == g[k].shape and np.array_equal(got, g[k]), k
+        n += 1
+    assert n == sum(len(m.store) for m in mats.values())
+    return n
+
+
+@pytest.mark.parametrize("name", ["qr_28_7", "qr_16_8", "qr_24_8"])
+def test_qr_program_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name + ".npz")
+    n, b = int(g["n"]), int(g["b"])
+    A = orc.OracleBigMatrix("A", (n, n), (b, b)); orc.shard_matrix(A, g["X"])
+    Rs, Vs, Ts, S = orc.run_qr(A)
+    assert _check_tiles(g, {"Vs": Vs, "Ts": Ts, "Rs": Rs, "Ss": S}) > 0
+
+
+@pytest.mark.parametrize("name", ["bdfac_16_4", "bdfac_16_4_trunc2", "bdfac_15_5"])
+def test_bdfac_program_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name + ".npz")
+    n, b, trunc = int(g["n"]), int(g["b"]), int(g["truncate"])
+    A = orc.OracleBigMatrix("A", (n, n), (b, b)); orc.shard_matrix(A, g["X"])
+    mats = orc.run_bdfac(A, truncate=trunc)
+    assert _check_tiles(g, mats) > 0
+
+
+@pytest.mark.parametrize("n,b", [(28, 7), (16, 8), (24, 8), (96, 48)])
+def test_qr_householder_semantics_meet_the_reference_test(n, b):
+    """tests/test_alg_correctness.py:160-187: the last diagonal block of R equals np.linalg.qr's up to row signs —
+    and so does every other block row."""
+    X = np.random.RandomState(n).randn(n, n)
+    A = orc.OracleBigMatrix("A", (n, n), (b, b)); orc.shard_matrix(A, X)
+    Rs, _, _, _ = orc.run_qr(A, semantics="householder")
+    nb = n // b
+    R = np.zeros((n, n))
+    for i in range(nb):
+        R[i * b:(i + 1) * b, i * b:(i + 1) * b] = Rs.get_block(i, i, 0)
+        for k in range(i + 1, nb):
+            R[i * b:(i + 1) * b, k * b:(k + 1) * b] = Rs.get_block(i, k, 0)
+    Rnp = np.linalg.qr(X)[1]
+    np.testing.assert_allclose(np.abs(R), np.abs(Rnp), rtol=1e-9, atol=1e-11)
+
+
+@pytest.mark.parametrize("n,b", [(16, 4), (15, 5), (48, 8)])
+def test_bdfac_householder_semantics_meet_the_reference_test(n, b):
+    """tests/test_alg_correctness.py:262-270: the block-bidiagonal factor has the singular values of the input."""
+    X = np.random.RandomState(n + 1).randn(n, n)
+    A = orc.OracleBigMatrix("A", (n, n), (b, b)); orc.shard_matrix(A, X)
+    m = orc.run_bdfac(A, semantics="householder")
+    fac = orc.bdfac_assemble(m["R_QR"], m["L_LQ"], n, b)
+    np.testing.assert_allclose(np.linalg.svd(fac, compute_uv=False), np.linalg.svd(X, compute_uv=False), rtol=1e-10, atol=1e-12)

@@ -1,0 +1,193 @@
+"""QR / BDFAC programs and the QR/LQ update kernels on the B200 (SURVEY §8 f#1, f#3): the GPU twin of
+tests/test_qr_programs_host.py — same golden fixtures from the unmodified reference ("reference" semantics), same
+criteria from the reference's own tests ("householder" semantics) — through libnpw_b200 and the stream engine
+(alg_wrappers.qr / bdfac + lambdapack_run, the call pattern of reference tests/test_alg_correctness.py:160-187, 216-275).
+Tolerance: 1e-10 relative (fp64; the blocked GPU summation order differs from LAPACK's)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from numpywren_b200 import alg_wrappers, job_runner, kernels, qr
+from numpywren_b200 import lambdapack as lp
+from numpywren_b200.matrix import BigMatrix
+from numpywren_b200.matrix_init import shard_matrix
+from oracle import npw_oracle as orc
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+def close(got, want, tol=TOL):
+    got = got.cpu().numpy() if isinstance(got, torch.Tensor) else np.asarray(got)
+    assert got.shape == want.shape, (got.shape, want.shape)
+    scale = max(1.0, np.abs(want).max())
+    assert np.abs(got - want).max() <= tol * scale, np.abs(got - want).max()
+
+
+@pytest.fixture
+def semantics():
+    prev = qr.get_qr_semantics()
+    yield qr.set_qr_semantics
+    qr.set_qr_semantics(prev)
+
+
+def run(program):
+    program.start()
+    out = job_runner.lambdapack_run(program, timeout=300)
+    assert program.program_status() == lp.PS.SUCCESS
+    return out
+
+
+@pytest.mark.parametrize("tag", ["s", "l"])
+def test_update_kernels_reference_semantics(golden_dir, cuda_device, semantics, tag):
+    g = np.load(os.path.join(golden_dir, "qr_kernels.npz"))
+    D = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    semantics("reference")
+    v, t, r = kernels.qr_factor_triangular(D(g[f"{tag}_r0"]), D(g[f"{tag}_r1"]))
+    close(v, g[f"{tag}_tri_v"]); close(t, g[f"{tag}_tri_t"]); close(r, g[f"{tag}_tri_r"])
+    close(kernels.qr_leaf(D(g[f"{tag}_vq"]), D(g[f"{tag}_tq"]), D(g[f"{tag}_a"])), g[f"{tag}_leaf"])
+    s01, s11 = kernels.qr_trailing_update(D(g[f"{tag}_vm"]), D(g[f"{tag}_tm"]), D(g[f"{tag}_s0"]), D(g[f"{tag}_s1"]))
+    close(s01, g[f"{tag}_s01"]); close(s11, g[f"{tag}_s11"])
+    n = g[f"{tag}_a"].shape[0]
+    wide = g[f"{tag}_wide"]
+    vl, tl, ll = kernels.lq_factor(D(wide[:, :n]), D(wide[:, n:]))
+    close(vl, g[f"{tag}_vl"]); close(tl, g[f"{tag}_tl"]); close(ll, g[f"{tag}_ll"])
+    l01, l11 = kernels.lq_trailing_update(vl, tl, D(g[f"{tag}_c0"]), D(g[f"{tag}_c1"]))
+    close(l01, g[f"{tag}_l01"]); close(l11, g[f"{tag}_l11"])
+    close(kernels.lq_leaf(D(g[f"{tag}_vl1"]), D(g[f"{tag}_tl1"]), D(g[f"{tag}_c0"])), g[f"{tag}_lqleaf"])
+
+
+@pytest.mark.parametrize("n", [8, 40, 130, 512])
+def test_triangular_merge_householder_semantics(cuda_device, semantics, n):
+    rs = np.random.RandomState(n)
+    semantics("householder")
+    r0, r1 = np.triu(rs.randn(n, n)), np.triu(rs.randn(n, n))
+    junk0 = r0 + np.tril(rs.randn(n, n), -1)          # dtpqrt never reads below the diagonals
+    junk1 = r1 + np.tril(rs.randn(n, n), -1)
+    D = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    v2, t, r = kernels.qr_factor_triangular(D(junk0), D(junk1))
+    vo, to, ro = orc.qr_factor_triangular(r0, r1, "householder")
+    close(v2, vo); close(t, to); close(r, ro)
+
+
+@pytest.mark.parametrize("m,c", [(96, 40), (512, 384)])
+def test_leaf_and_trailing_updates_householder_semantics(cuda_device, semantics, m, c):
+    """Both code paths of kernels._gemm_any: generic kernel (small) and transpose + DMMA NT core (large), with
+    strided and stored-transposed operands."""
+    rs = np.random.RandomState(m)
+    semantics("householder")
+    D = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    a = rs.randn(m, m)
+    vo, to, ro = orc.qr_factor(a)
+    s0 = rs.randn(c, m)                                # used as s0.T: stored transposed
+    close(kernels.qr_leaf(D(vo), D(to), D(s0).T), orc.qr_leaf(vo, to, s0.T, "householder"))
+    r0, r1 = np.triu(rs.randn(m, m)), np.triu(rs.randn(m, m))
+    vm, tm, _ = orc.qr_factor(r0, r1)
+    t0, t1 = rs.randn(m, c), rs.randn(m, c)
+    big = D(np.hstack([t0, t1]))                       # column slices: leading dimension 2c
+    s01, s11 = kernels.qr_trailing_update(D(vm), D(tm), big[:, :c], big[:, c:])
+    o01, o11 = orc.qr_trailing_update(vm, tm, t0, t1)
+    close(s01, o01); close(s11, o11)
+    wide = rs.randn(m, 2 * m)
+    vl, tl, ll = orc.lq_factor(wide[:, :m], wide[:, m:])
+    c0, c1 = rs.randn(m, m), rs.randn(m, m)
+    l01, l11 = kernels.lq_trailing_update(D(vl), D(tl), D(c0), D(c1))
+    p01, p11 = orc.lq_trailing_update(vl, tl, c0, c1)
+    close(l01, p01); close(l11, p11)
+    vl1, tl1, _ = orc.lq_factor(a)
+    close(kernels.lq_leaf(D(vl1), D(tl1), D(c0)), orc.lq_leaf(vl1, tl1, c0))
+    gv, gt, gl = kernels.lq_factor(D(wide[:, :m]), D(wide[:, m:]))
+    close(gv, vl); close(gt, tl); close(gl, ll)
+
+
+def _bigmatrix(name, X, b):
+    A = BigMatrix(name, shape=X.shape, shard_sizes=(b, b))
+    A.free()
+    shard_matrix(A, X)
+    return A
+
+
+def _check_against_golden(g, mats):
+    n = 0
+    for k in g.files:
+        name = next((m for m in mats if k.startswith(m + "_")), None)
+        if name is None:
+            continue
+        idx = tuple(int(x) for x in k[len(name) + 1:].split("_"))
+        got = mats[name]._blocks_store[idx].cpu().numpy()
+        close(got.reshape(g[k].shape), g[k])
+        n += 1
+    assert n == sum(len(m._blocks_store) for m in mats.values())
+    return n
+
+
+@pytest.mark.parametrize("name", ["qr_28_7", "qr_16_8", "qr_24_8"])
+def test_qr_program_reference_semantics_matches_golden(golden_dir, unique_key, cuda_device, semantics, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    semantics("reference")
+    A = _bigmatrix(unique_key("qrA"), g["X"], int(g["b"]))
+    program, meta = alg_wrappers.qr(A)
+    mats = dict(zip(["Rs", "Vs", "Ts", "Ss"], meta["outputs"] + meta["intermediates"]))
+    for m in mats.values():
+        m.free()
+    res = run(program)
+    assert len(res["executed_messages"]) == int(g["nnodes"])
+    assert _check_against_golden(g, mats) > 0
+    for m in list(mats.values()) + [A]:
+        m.free()
+
+
+@pytest.mark.parametrize("name", ["bdfac_16_4", "bdfac_16_4_trunc2", "bdfac_15_5"])
+def test_bdfac_program_reference_semantics_matches_golden(golden_dir, unique_key, cuda_device, semantics, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    semantics("reference")
+    A = _bigmatrix(unique_key("bdA"), g["X"], int(g["b"]))
+    program, meta = alg_wrappers.bdfac(A, truncate=int(g["truncate"]))
+    mats = dict(zip(["L_LQ", "R_QR", "S_LQ", "S_QR", "T_QR", "V_QR", "V_LQ", "T_LQ"], meta["outputs"] + meta["intermediates"]))
+    for m in mats.values():
+        m.free()
+    res = run(program)
+    assert len(res["executed_messages"]) == int(g["nnodes"])
+    assert _check_against_golden(g, mats) > 0
+    for m in list(mats.values()) + [A]:
+        m.free()
+
+
+@pytest.mark.parametrize("n,b", [(28, 7), (192, 64), (1024, 256)])
+def test_qr_program_householder_semantics_meets_reference_test(unique_key, cuda_device, semantics, n, b):
+    """tests/test_alg_correctness.py:160-187 (R equals np.linalg.qr's up to row signs), every block row."""
+    semantics("householder")
+    X = np.random.RandomState(n).randn(n, n)
+    A = _bigmatrix(unique_key("qrA"), X, b)
+    program, meta = alg_wrappers.qr(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    run(program)
+    Rs = meta["outputs"][0]
+    nb = n // b
+    R = np.zeros((n, n))
+    for i in range(nb):
+        for k in range(i, nb):
+            R[i * b:(i + 1) * b, k * b:(k + 1) * b] = Rs.get_block(i, k, 0).cpu().numpy()
+    close(np.abs(R), np.abs(np.linalg.qr(X)[1]), 1e-9)
+    for m in meta["outputs"] + meta["intermediates"] + [A]:
+        m.free()
+
+
+@pytest.mark.parametrize("n,b", [(16, 4), (15, 5), (512, 128)])
+def test_bdfac_program_householder_semantics_meets_reference_test(unique_key, cuda_device, semantics, n, b):
+    """tests/test_alg_correctness.py:262-270: the block-bidiagonal factor keeps the singular values."""
+    semantics("householder")
+    X = np.random.RandomState(n + 1).randn(n, n)
+    A = _bigmatrix(unique_key("bdA"), X, b)
+    program, meta = alg_wrappers.bdfac(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    run(program)
+    L, R = meta["outputs"]
+    fac = orc.bdfac_assemble(R, L, n, b, get=lambda m, *idx: m.get_block(*idx).cpu().numpy())
+    close(np.linalg.svd(fac, compute_uv=False), np.linalg.svd(X, compute_uv=False), 1e-10)
+    for m in meta["outputs"] + meta["intermediates"] + [A]:
+        m.free()
