@@ -102,7 +102,7 @@ class TileEngine:
     """Executes ready nodes of one LambdaPackProgram on one GPU (one process = one GPU)."""
 
     def __init__(self, program: lp.LambdaPackProgram, streams: int = 4, high_streams: int = 2, inplace: bool = True,
-                 consume_inputs: bool = False, profile: bool = False, comm=None):
+                 consume_inputs: bool = False, profile: bool = False, comm=None, free_intermediates: bool = False):
         self.program = program
         self.compiled = program.program
         self.inplace = inplace
@@ -122,6 +122,14 @@ class TileEngine:
         self._prio: Optional[List[int]] = None
         self._lower_ok: Dict[int, bool] = {}
         self.skip_upper = os.environ.get("NPW_B200_SKIP_UPPER", "1") != "0"
+        # dead-tile reclamation (opt-in): an SSA intermediate is dropped from the HBM store as soon as its last reader
+        # has been enqueued.  The reference keeps every version in S3 for ever; in HBM the QR / BDFAC / GEMM programs'
+        # intermediates would otherwise outgrow the device (GEMM Temp: M*N*K tiles).  Single-GPU engine only.
+        self.free_intermediates = free_intermediates and comm is None
+        self._keep_mats = {id(self.compiled.scope[n]) for n in list(self.compiled.inputs) + list(self.compiled.outputs)
+                           if n in self.compiled.scope}
+        self._reads_left: Dict[Any, int] = {}
+        self.freed_tiles = 0
 
     # ------------------------------------------------------------------ priorities
     def priorities(self) -> List[int]:
@@ -222,6 +230,8 @@ class TileEngine:
             # default tile (parent_fn), transposed view, or diagonal shift: the public path makes a private copy
             tile = m.get_block(*idx)
             return tile, None, key, True
+        if self.free_intermediates and id(m) not in self._keep_mats:
+            ref.record_stream(stream)      # the allocator must not recycle the buffer before this stream is done with it
         tile = ref.squeeze() if m.autosqueeze else ref
         return tile, ref, key, False
 
@@ -310,6 +320,8 @@ class TileEngine:
                 t1 = torch.cuda.Event(enable_timing=True)
                 t1.record(stream)
                 self.timeline.append((node, t0, t1, id(stream)))
+            if self.free_intermediates:
+                self._release_dead_inputs(node, refs, keys, consumed)
         self.launched += 1
         # counters (reference job_runner.py:236-237, 265-266, 293-296)
         prog = self.program
@@ -323,6 +335,24 @@ class TileEngine:
             prog.incr_read(lp._nbytes(m))
         for (m, _) in node.writes:
             prog.incr_write(lp._nbytes(m))
+
+    def _release_dead_inputs(self, node, refs, keys, consumed):
+        """Drop stored intermediates whose every reader has now been enqueued (stream order + record_stream keep the
+        memory alive until the kernels that were given the pointer have run)."""
+        written = {_tile_key(m, idx) for m, idx in node.writes}
+        for j, (m, idx) in enumerate(node.reads):
+            if refs[j] is None or id(m) in self._keep_mats or j == consumed:
+                continue
+            key = keys[j]
+            left = self._reads_left.get(key)
+            if left is None:
+                left = self.compiled.num_readers(m, idx)
+            left -= 1
+            self._reads_left[key] = left
+            if left <= 0 and key not in written:
+                m.delete_block(*idx)
+                self.tile_event.pop(key, None)
+                self.freed_tiles += 1
 
     # ------------------------------------------------------------------ drain
     def finish(self):
@@ -365,7 +395,7 @@ def _engine_for(program: lp.LambdaPackProgram, **opts) -> TileEngine:
 
 def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, timeout=200, idle_timeout=5,
                    msg_vis_timeout_jitter=15, compute_threads=1, streams=None, high_streams=None, inplace=None,
-                   consume_inputs=False, profile=False):
+                   consume_inputs=False, profile=False, free_intermediates=None):
     """Run ready nodes of ``program`` until it finishes, fails, or ``timeout`` seconds elapse.
 
     Signature and return keys follow reference job_runner.lambdapack_run (:316-370).  ``pipeline_width``
@@ -389,8 +419,10 @@ def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, 
     n_high = high_streams if high_streams is not None else int(os.environ.get("NPW_B200_HIGH_STREAMS", 2))
     if inplace is None:
         inplace = os.environ.get("NPW_B200_INPLACE", "1") != "0"
+    if free_intermediates is None:
+        free_intermediates = os.environ.get("NPW_B200_FREE_INTERMEDIATES", "0") != "0"
     eng = _engine_for(program, streams=n_streams, high_streams=n_high, inplace=inplace, consume_inputs=consume_inputs,
-                      profile=profile)
+                      profile=profile, free_intermediates=free_intermediates)
     program._defer_success = True
     executed, refs = [], []
     try:

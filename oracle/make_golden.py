@@ -406,6 +406,18 @@ def structure_counts(ref):
         prog = comp.lpcompile(algs.TSQR)(dummy(2), dummy(2), dummy(2), dummy(2), N)
         out[f"tsqr_{N}"] = {"nodes": len(comp.walk_program(prog)), "starters": len(comp.find_starters(prog, ["A"])),
                             "terminators": len(comp.find_terminators(prog, ["Rs"]))}
+    # QR / BDFAC: node counts where walk_program is affordable, starters/terminators also at the reference test's
+    # size (tests/test_starters_terminators.py:22-31 uses M = 256; its literal 129920 predates the current QR program,
+    # the current reference code gives the number recorded here)
+    for N in (2, 3, 4, 8, 32, 256):
+        prog = comp.lpcompile(algs.QR)(dummy(2), dummy(3), dummy(3), dummy(3), dummy(4), N, 0)
+        out[f"qr_{N}"] = {"nodes": len(comp.walk_program(prog)) if N <= 8 else None,
+                          "starters": len(comp.find_starters(prog, ["I"])), "terminators": len(comp.find_terminators(prog, ["Rs"]))}
+    for N in (2, 3, 4, 5, 8):
+        prog = comp.lpcompile(algs.BDFAC)(dummy(2), dummy(3), dummy(3), dummy(4), dummy(3), dummy(3), dummy(3), dummy(4),
+                                          dummy(3), N, 0)
+        out[f"bdfac_{N}"] = {"nodes": len(comp.walk_program(prog)), "starters": len(comp.find_starters(prog, ["I"])),
+                             "terminators": len(comp.find_terminators(prog, ["R_QR", "L_LQ"]))}
     return out
 
 

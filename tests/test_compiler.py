@@ -79,6 +79,29 @@ def test_gemm_and_tsqr_counts_match_reference(structure):
                 (ref["nodes"], ref["starters"], ref["terminators"]), name
 
 
+def test_qr_and_bdfac_counts_match_reference(structure):
+    """Starters / terminators (and node counts) of algs.QR and algs.BDFAC as the reference's compiler reports them,
+    including the size of its own known-answer test (tests/test_starters_terminators.py:22-31, M = 256)."""
+    seen = 0
+    for name, ref in structure["structure"].items():
+        if name.startswith("qr_"):
+            N = int(name.split("_")[1])
+            p = compiler.lpcompile(algs.QR)(dummy_matrix(), dummy_matrix(3), dummy_matrix(3), dummy_matrix(3), dummy_matrix(4), N, 0)
+            assert len(compiler.find_starters(p, ["I"])) == ref["starters"] == N, name
+            assert len(compiler.find_terminators(p, ["Rs"])) == ref["terminators"], name
+            if ref["nodes"] is not None:
+                assert len(compiler.walk_program(p)) == ref["nodes"], name
+            seen += 1
+        elif name.startswith("bdfac_"):
+            N = int(name.split("_")[1])
+            p = compiler.lpcompile(algs.BDFAC)(dummy_matrix(), dummy_matrix(3), dummy_matrix(3), dummy_matrix(4), dummy_matrix(3),
+                                               dummy_matrix(3), dummy_matrix(3), dummy_matrix(4), dummy_matrix(3), N, 0)
+            assert (len(compiler.walk_program(p)), len(compiler.find_starters(p, ["I"])),
+                    len(compiler.find_terminators(p, ["R_QR", "L_LQ"]))) == (ref["nodes"], ref["starters"], ref["terminators"]), name
+            seen += 1
+    assert seen >= 11
+
+
 @pytest.mark.parametrize("which", ["cholesky_64_16", "gemm_64_16", "tsqr_256_32", "qr_28_7", "bdfac_16_4"])
 def test_dag_edges_equal_reference_symbolic_analysis(structure, which):
     dag = structure[which]["dag"]

@@ -191,3 +191,52 @@ def test_bdfac_program_householder_semantics_meets_reference_test(unique_key, cu
     close(np.linalg.svd(fac, compute_uv=False), np.linalg.svd(X, compute_uv=False), 1e-10)
     for m in meta["outputs"] + meta["intermediates"] + [A]:
         m.free()
+
+
+def test_dead_intermediates_are_reclaimed(unique_key, cuda_device, semantics):
+    """free_intermediates=True drops every SSA intermediate once its last reader is enqueued: same R, and the store
+    of S holds (almost) nothing at the end instead of one tile per trailing update."""
+    semantics("householder")
+    n, b = 512, 64
+    X = np.random.RandomState(9).randn(n, n)
+    outs = []
+    for free in (False, True):
+        A = _bigmatrix(unique_key("qrA"), X, b)
+        program, meta = alg_wrappers.qr(A)
+        for m in meta["outputs"] + meta["intermediates"]:
+            m.free()
+        program.start()
+        job_runner.lambdapack_run(program, timeout=300, free_intermediates=free)
+        assert program.program_status() == lp.PS.SUCCESS
+        Rs, S = meta["outputs"][0], meta["intermediates"][0]
+        nb = n // b
+        R = np.zeros((n, n))
+        for i in range(nb):
+            for k in range(i, nb):
+                R[i * b:(i + 1) * b, k * b:(k + 1) * b] = Rs.get_block(i, k, 0).cpu().numpy()
+        outs.append((R, len(S._blocks_store), program._engine.freed_tiles))
+        for m in meta["outputs"] + meta["intermediates"] + [A]:
+            m.free()
+    (R0, kept0, freed0), (R1, kept1, freed1) = outs
+    assert np.array_equal(R0, R1)
+    assert freed0 == 0 and freed1 > 0 and kept1 < kept0 // 4
+    close(np.abs(R1), np.abs(np.linalg.qr(X)[1]), 1e-9)
+
+
+def test_gemm_program_with_reclaimed_temporaries(unique_key, cuda_device):
+    """The DSL GEMM's M*N*K partial products (Temp) are freed as the add tree consumes them."""
+    from numpywren_b200.alg_wrappers import gemm
+    n, b = 512, 128
+    rs = np.random.RandomState(10)
+    a, bm = rs.randn(n, n), rs.randn(n, n)
+    A = _bigmatrix(unique_key("gA"), a, b)
+    B = _bigmatrix(unique_key("gB"), bm, b)
+    program, meta = gemm(A, B)
+    program.start()
+    job_runner.lambdapack_run(program, timeout=300, free_intermediates=True)
+    assert program.program_status() == lp.PS.SUCCESS
+    C = meta["outputs"][0].numpy()
+    assert np.linalg.norm(C - a @ bm) / np.linalg.norm(a @ bm) < 1e-13
+    assert program._engine.freed_tiles > 0 and len(meta["intermediates"][0]._blocks_store) == 0
+    for m in meta["outputs"] + meta["intermediates"] + [A, B]:
+        m.free()
