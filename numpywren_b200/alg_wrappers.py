@@ -103,10 +103,21 @@ def gemm(A, B):
     return program, {"outputs": [C_sharded], "intermediates": [Temp], "compile_time": c_time}
 
 
-def _loose(key, X, shape, shard_sizes, parent_fn=None):
-    """Intermediate of the QR/BDFAC programs: over-allocated index space, shape checks off (safe=False)."""
-    return BigMatrix(key, shape=shape, shard_sizes=shard_sizes, bucket=X.bucket, write_header=True, parent_fn=parent_fn,
-                     safe=False, device=X.device)
+def _loose(key, X, shape, shard_sizes, parent_fn=None, place_axis=None, tile_shape=None):
+    """Intermediate of the QR/BDFAC programs: over-allocated index space, shape checks off (safe=False).
+
+    Multi-GPU placement: 1-D cyclic over ALL ranks by the block index along ``place_axis`` (block column for the QR
+    sweeps, block row for the LQ sweeps).  A tree node's update kernels write TWO tiles of one block column (row); the
+    engine runs a node where its first output lives, so both outputs must share an owner — a 1-D map guarantees it,
+    the 2-D block-cyclic map of the Cholesky would not.  ``tile_shape(idx)`` declares the stored tile's shape where the
+    loose allocation's block shape says nothing (receivers size their NVLink inbox slots from it)."""
+    m = BigMatrix(key, shape=shape, shard_sizes=shard_sizes, bucket=X.bucket, write_header=True, parent_fn=parent_fn,
+                  safe=False, device=X.device)
+    if place_axis is not None:
+        m.placement = lambda true_idx, ax=place_axis: (0, int(true_idx[ax]))
+    if tile_shape is not None:
+        m.tile_shape = tile_shape
+    return m
 
 
 def qr(A):
@@ -117,10 +128,13 @@ def qr(A):
     N_blocks = A.num_blocks(0)
     shard_size = A.shard_sizes[0]
     num_tree_levels = max(int(np.ceil(np.log2(A.num_blocks(0)) / np.log2(b_fac))), 1) + 1
-    Vs = _loose("Vs", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros)
-    Ts = _loose("Ts", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros)
-    Rs = _loose("Rs", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros)
-    Ss = _loose("Ss", A, (2 * N, 2 * N, 2 * N, num_tree_levels * shard_size), (shard_size, shard_size, 1, 1), constant_zeros)
+    sq = lambda idx: (shard_size, shard_size)            # every tile of the QR program is shard x shard
+    # Vs/Ts/Rs[j, i, level] belong to panel (block column) i; S[j, k, i, level] to trailing block column k
+    Vs = _loose("Vs", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros, 1, sq)
+    Ts = _loose("Ts", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros, 1, sq)
+    Rs = _loose("Rs", A, (2 * N, 2 * N, num_tree_levels), (shard_size, shard_size, 1), constant_zeros, 1, sq)
+    Ss = _loose("Ss", A, (2 * N, 2 * N, 2 * N, num_tree_levels * shard_size), (shard_size, shard_size, 1, 1), constant_zeros,
+                1, sq)
     t = time.time()
     p0 = lpcompile_for_execution(QR, inputs=["I"], outputs=["Rs"])
     p1 = p0(A, Vs, Ts, Rs, Ss, N_blocks, 0)
@@ -138,14 +152,20 @@ def bdfac(A, truncate=0):
     N_blocks = A.num_blocks(0)
     shard_size = A.shard_sizes[0]
     num_tree_levels = max(int(np.ceil(np.log2(A.num_blocks(0)) / np.log2(b_fac))), 1) + 1
-    V_QR = _loose("V_QR", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size))
-    T_QR = _loose("T_QR", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size))
-    R_QR = _loose("R_QR", A, (2 * N, num_tree_levels, 2 * N), (shard_size, 1, shard_size), constant_zeros)
-    S_QR = _loose("S_QR", A, (2 * N, num_tree_levels, 2 * N, 2 * N), (1, 1, shard_size, shard_size), constant_zeros)
-    V_LQ = _loose("V_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size))
-    T_LQ = _loose("T_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size))
-    L_LQ = _loose("L_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size), constant_zeros_ext)
-    S_LQ = _loose("S_LQ", A, (2 * N, num_tree_levels, 2 * N, 2 * N), (1, 1, shard_size, shard_size), constant_zeros_ext)
+    b = shard_size
+    sq = lambda idx: (b, b)
+    tall = lambda idx: (b, b) if idx[1] == 0 else (2 * b, b)     # V of a tree merge stacks two R factors
+    wide = lambda idx: (b, b) if idx[1] == 0 else (b, 2 * b)     # ... and its LQ mirror puts two L factors side by side
+    # QR sweep of stage i: factors (index [i, level, j]) live with panel i, S_QR[i, level, j, k] with block column k;
+    # LQ sweep: factors ([i, level, k]) with stage i, S_LQ[i, level, j, k] with block row j
+    V_QR = _loose("V_QR", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size), None, 0, tall)
+    T_QR = _loose("T_QR", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size), None, 0, sq)
+    R_QR = _loose("R_QR", A, (2 * N, num_tree_levels, 2 * N), (shard_size, 1, shard_size), constant_zeros, 0, sq)
+    S_QR = _loose("S_QR", A, (2 * N, num_tree_levels, 2 * N, 2 * N), (1, 1, shard_size, shard_size), constant_zeros, 3, sq)
+    V_LQ = _loose("V_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size), None, 0, wide)
+    T_LQ = _loose("T_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size), None, 0, sq)
+    L_LQ = _loose("L_LQ", A, (2 * N, num_tree_levels, 2 * N), (1, 1, shard_size), constant_zeros_ext, 0, sq)
+    S_LQ = _loose("S_LQ", A, (2 * N, num_tree_levels, 2 * N, 2 * N), (1, 1, shard_size, shard_size), constant_zeros_ext, 2, sq)
     t = time.time()
     p0 = lpcompile_for_execution(BDFAC, inputs=["I"], outputs=["R_QR", "L_LQ"])
     p1 = p0(A, V_QR, T_QR, S_QR, R_QR, V_LQ, T_LQ, S_LQ, L_LQ, N_blocks, truncate)

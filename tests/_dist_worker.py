@@ -86,6 +86,38 @@ def main():
         mine_slots = sorted(v for (k, dst), v in slot.items() if dst == d)
         assert mine_slots == list(range(len(mine_slots))) and len(mine_slots) <= max_slots
 
+    # ---- QR / BDFAC: nodes with two outputs (the tree's trailing updates) must find both output tiles on one rank,
+    #      and their transfer plans must pair up like the Cholesky's
+    from numpywren_b200 import alg_wrappers
+    for which in ("qr", "bdfac"):
+        Xq = BigMatrix("dist_%s_in" % which, shape=(24, 24), shard_sizes=(4, 4), device="cpu")
+        program, meta = getattr(alg_wrappers, which)(Xq)
+        cp = program.program
+        qplan = parallel.TransferPlan(cp, grid)
+        multi = 0
+        for n in cp.nodes:
+            owners = {grid.owner(m, idx) for m, idx in n.writes}
+            assert len(owners) == 1, (which, n, owners)
+            multi += len(n.writes) > 1
+        assert multi > 0
+        counts = [0] * world
+        for r in qplan.exec_rank:
+            counts[r] += 1
+        assert min(counts) > 0                                            # every rank gets work
+        qs = [None] * world
+        dist.all_gather_object(qs, qplan.describe(rank))
+        for a in range(world):
+            for b in range(world):
+                if a != b:
+                    assert [k for (op, k, peer) in qs[a] if op == "send" and peer == b] == \
+                        [k for (op, k, peer) in qs[b] if op == "recv" and peer == a], (which, a, b)
+        # inbox slots can be sized: every transferred tile has a declared shape
+        slot, slot_elems, max_slots = qplan.assign_inbox_slots()
+        assert slot_elems >= 16 and len(slot) == qplan.num_transfers
+        for lst in list(qplan.after_node.values()) + list(qplan.before_node.values()):
+            for key, m, idx, src, dst in lst:
+                assert int(np.prod(parallel._tile_shape(m, idx))) in (16, 32), (which, m.key, idx)
+
     # ---- failure agreement helper
     assert parallel.allreduce_max_int(rank * 3, torch.device("cpu")) == (world - 1) * 3
     dist.barrier()
