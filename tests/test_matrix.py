@@ -189,3 +189,30 @@ def test_convert_to_slice():
     assert convert_to_slice([1, 5, 2]) == slice(1, 5, 2)
     with pytest.raises(ValueError):
         convert_to_slice([1, 2, 3, 4])
+
+
+# ------------------------------------------------------------------ reshard_down (reference tests/test_reshard.py:12-48)
+@pytest.mark.parametrize("shape,shards,breaks", [((128, 128), (128, 128), (4, 4)), ((128, 128), (64, 64), (4, 4)),
+                                                  ((100, 72), (64, 48), (2, 3))])
+def test_reshard_down_matrix(unique_key, shape, shards, breaks):
+    from numpywren_b200.matrix_init import reshard_down
+    X = np.random.RandomState(0).randn(*shape)
+    A = BigMatrix(unique_key("rs"), shape=shape, shard_sizes=shards, device="cpu")
+    shard_matrix(A, X)
+    B = reshard_down(A, breaks)
+    assert tuple(B.shard_sizes) == tuple(s // k for s, k in zip(shards, breaks))
+    assert np.all(A.numpy() == X) and np.all(B.numpy() == X)
+    assert B.get_block(0, 0).shape == tuple(min(s // k, n) for s, k, n in zip(shards, breaks, shape))
+    A.free(); B.free()
+
+
+def test_reshard_down_tensor(unique_key):
+    from numpywren_b200.matrix_init import reshard_down
+    X = np.random.RandomState(1).randn(128, 128, 4)
+    A = BigMatrix(unique_key("rs3"), shape=X.shape, shard_sizes=(64, 64, 4), device="cpu")
+    A.autosqueeze = False
+    shard_matrix(A, X)
+    B = reshard_down(A, (4, 4, 2), pwex=None)
+    assert np.all(A.numpy() == X) and np.all(B.numpy() == X)
+    assert tuple(B.get_block(0, 0, 0).shape) == (16, 16, 2)
+    A.free(); B.free()
