@@ -165,6 +165,22 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt,
                   const double* A, int64_t lda, int64_t m, int64_t n,
                   void* work, npw_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * kernels.qr_factor_triangular(x0, x1) -> (V, T, R)  (kernels.py:132-134 →
+ * fast_qr_triangular :107-124: LAPACK dtpqrt with m = n, l = m).  QR of
+ * [triu(R0); triu(R1)] for two n x n factors (only their upper triangles are
+ * read).  Outputs: V2 (n x n upper triangular: the bottom half of the
+ * reflectors, Q = I - [I; V2] T [I; V2]^T), T (n x n upper, the single
+ * compact-WY factor, i.e. dtpqrt with nb = n), R (n x n upper).  The Python shim
+ * derives the reference's literal return values from these (qr.py).
+ * `work`: npw_tpqrt_work_bytes(n).  No output may alias an input.
+ * ---------------------------------------------------------------------- */
+size_t npw_tpqrt_work_bytes(int64_t n);
+int npw_tpqrt_f64(double* V2, int64_t ldv, double* T, int64_t ldt,
+                  double* R, int64_t ldr,
+                  const double* R0, int64_t ld0, const double* R1, int64_t ld1,
+                  int64_t n, void* work, npw_stream_t stream);
+
 /* Device-side synthetic tile generator used by bench/tests (not a reference
  * op): counter-based uniform(-1,1) fill, reproducible from (seed, row, col). */
 int npw_fill_random_f64(double* A, int64_t lda, int64_t rows, int64_t cols,

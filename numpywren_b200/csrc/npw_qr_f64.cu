@@ -493,4 +493,45 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
   return NPW_OK;
 }
 
+size_t npw_tpqrt_work_bytes(int64_t n) {
+  if (n <= 0) return 0;
+  return npw::align256(static_cast<size_t>(2 * n) * n * sizeof(double)) + npw_geqrt_work_bytes(2 * n, n);
+}
+
+// QR of two stacked upper-triangular factors.  Column j of [triu(R0); triu(R1)] has non-zeros in row j of the top block
+// and rows 0..j of the bottom block only, so the general panel factorisation of the 2n x n stack produces exactly
+// dtpqrt's reflectors: top half of V = I, bottom half = V2 (upper triangular), same T and R.
+int npw_tpqrt_f64(double* V2, int64_t ldv, double* T, int64_t ldt, double* R, int64_t ldr, const double* R0, int64_t ld0,
+                  const double* R1, int64_t ld1, int64_t n, void* work, npw_stream_t stream) {
+  using namespace npw;
+  if (n == 0) return NPW_OK;
+  if (!V2) return -1;
+  if (ldv < n) return -2;
+  if (!T) return -3;
+  if (ldt < n) return -4;
+  if (!R) return -5;
+  if (ldr < n) return -6;
+  if (!R0) return -7;
+  if (ld0 < n) return -8;
+  if (!R1) return -9;
+  if (ld1 < n) return -10;
+  if (n < 0 || 2 * n > INT32_MAX) return -11;
+  if (!work) return -12;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  double* W = static_cast<double*>(work);                       // the 2n x n stack, leading dimension n
+  double* Wlo = W + n * n;
+  void* qr_work = static_cast<char*>(work) + align256(static_cast<size_t>(2 * n) * n * sizeof(double));
+  int rc = launch_copy2d(W, n, R0, ld0, n, n, 0, st);
+  if (rc) return rc;
+  rc = launch_copy2d(Wlo, n, R1, ld1, n, n, 0, st);
+  if (rc) return rc;
+  rc = launch_fill2d(W, n, n, n, 1, 0.0, st);                   // dtpqrt reads the upper triangles only
+  if (rc) return rc;
+  rc = launch_fill2d(Wlo, n, n, n, 1, 0.0, st);
+  if (rc) return rc;
+  rc = npw_geqrt_f64(W, n, T, ldt, R, ldr, W, n, 2 * n, n, qr_work, stream);
+  if (rc) return rc;
+  return launch_copy2d(V2, ldv, Wlo, n, n, n, 0, st);
+}
+
 }  // extern "C"

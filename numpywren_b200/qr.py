@@ -99,22 +99,32 @@ def qr_factor(*blocks, **kwargs):
 
 
 def qr_factor_triangular(x0, x1, **kwargs):
-    """QR of [triu(x0); triu(x1)] for two n x n factors.  The stacked Householder QR has exactly dtpqrt's reflectors
-    (column j touches row j of the top block and rows 0..j of the bottom block only), so the structured LAPACK routine
-    and the general panel kernel agree; the structured flop saving (about 2x) is not exploited yet."""
+    """QR of [triu(x0); triu(x1)] for two n x n factors (npw_tpqrt_f64).  The stacked Householder QR has exactly
+    dtpqrt's reflectors (column j touches row j of the top block and rows 0..j of the bottom block only), so the
+    structured LAPACK routine and the general panel kernel agree; the structured flop saving (about 2x) is not
+    exploited yet."""
     _check_tile(x0, "x0")
     _check_tile(x1, "x1")
     n = x0.shape[1]
     if x0.shape[0] != n or tuple(x1.shape) != (n, n):
         raise ValueError(f"qr_factor_triangular expects two square tiles of equal size, got {tuple(x0.shape)} {tuple(x1.shape)}")
-    W = torch.empty((2 * n, n), dtype=torch.float64, device=x0.device)
-    _copy_into(W[:n], x0)
-    _copy_into(W[n:], x1)
-    _fill2d(W[:n], 1)   # dtpqrt reads only the upper triangles (l = m: B is upper triangular)
-    _fill2d(W[n:], 1)
-    W, T, R = _geqrt_inplace(W)
+    lib = _capi.load()
+    dev = x0.device
+    m0, ld0, tr0 = _mat(x0, "x0")
+    m1, ld1, tr1 = _mat(x1, "x1")
+    if tr0:
+        m0, ld0 = transpose(x0.T), n       # row-major copy (the entry point takes row-major factors)
+    if tr1:
+        m1, ld1 = transpose(x1.T), n
+    V2 = torch.empty((n, n), dtype=torch.float64, device=dev)
+    T = torch.empty((n, n), dtype=torch.float64, device=dev)
+    R = torch.empty((n, n), dtype=torch.float64, device=dev)
+    work = torch.empty(max(1, lib.npw_tpqrt_work_bytes(n) // 8), dtype=torch.float64, device=dev)
+    rc = lib.npw_tpqrt_f64(V2.data_ptr(), max(1, n), T.data_ptr(), max(1, n), R.data_ptr(), max(1, n), m0.data_ptr(), ld0,
+                           m1.data_ptr(), ld1, n, work.data_ptr(), _stream())
+    _capi.check(rc, "npw_tpqrt_f64")
     if _SEMANTICS == "householder":
-        return W[n:], T, R
+        return V2, T, R
     V = add_diag(_fill2d(torch.empty((n, n), dtype=torch.float64, device=x0.device), 0), 1.0)
     if n > _TPQRT_NB:
         Tb = _fill2d(torch.empty((n, n), dtype=torch.float64, device=x0.device), 0)

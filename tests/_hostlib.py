@@ -35,6 +35,9 @@ class HostLib:
     def npw_geqrt_work_bytes(self, m, n):
         return 8
 
+    def npw_tpqrt_work_bytes(self, n):
+        return 8
+
     # -- kernels (semantics: include/npw_b200.h)
     def npw_gemm_f64(self, C, ldc, C0, ldc0, A, lda, transA, B, ldb, transB, m, n, k, alpha, beta, stream):
         self.calls.append(("gemm", m, n, k, transA, transB))
@@ -90,6 +93,19 @@ class HostLib:
         v = np.tril(qr, -1)[:, :n]
         v[np.arange(n), np.arange(n)] = 1.0
         _view(V, m, n, ldv)[...] = v
+        _view(T, n, n, ldt)[...] = np.triu(t)
+        _view(R, n, n, ldr)[...] = np.triu(qr)[:n]
+        return 0
+
+
+    def npw_tpqrt_f64(self, V2, ldv, T, ldt, R, ldr, R0, ld0, R1, ld1, n, work, stream):
+        """include/npw_b200.h: QR of [triu(R0); triu(R1)] → V2 (bottom half of the reflectors), the single n x n T, R —
+        restated here with the general LAPACK QR of the explicit stack, the way the CUDA entry point computes it."""
+        self.calls.append(("tpqrt", n))
+        stack = np.vstack([np.triu(np.array(_view(R0, n, n, ld0))), np.triu(np.array(_view(R1, n, n, ld1)))])
+        qr, t, info = scipy.linalg.lapack.dgeqrt(n, np.asfortranarray(stack))
+        assert info == 0
+        _view(V2, n, n, ldv)[...] = qr[n:]
         _view(T, n, n, ldt)[...] = np.triu(t)
         _view(R, n, n, ldr)[...] = np.triu(qr)[:n]
         return 0
