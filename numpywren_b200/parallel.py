@@ -69,6 +69,10 @@ class ProcessGrid:
     def is_mine(self, matrix, idx) -> bool:
         return self.owner(matrix, idx) == self.rank
 
+    def owner_of_coords(self, a: int, b: int) -> int:
+        """Owner of a 2-D tile (a, b) under the default map (what ``owner`` computes for a plain 2-D BigMatrix)."""
+        return ((a + b // self.Q) % self.P) * self.Q + (b % self.Q)
+
 
 def set_grid(grid: Optional[ProcessGrid]):
     global _GRID
@@ -420,10 +424,15 @@ def bench_main(args, metric, unit, workload):
                     A._put_block_ref(t, j, k)
         return A
 
+    plan_s = [0.0]
+
     def step(i):
         A = make_input(i)
         program, meta = cholesky(A)
         _ = program.program.nodes
+        # static DAG analysis (expansion above; priorities, transfer plan, inbox slots here) is done before the timed
+        # region and reported as config.dag_expand_s / config.plan_s — SURVEY §8d: "DAG pre-expanded"
+        plan_s[0] = job_runner.prepare(program, streams=args.streams, consume_inputs=True)
         torch.cuda.synchronize()
         dist.barrier(device_ids=[device.index])
         l0 = _capi.launch_count()
@@ -441,6 +450,30 @@ def bench_main(args, metric, unit, workload):
         eng = program._engine
         sent = eng.comm.bytes_sent if eng.comm is not None else 0
         return float(ms.item()), int(launches.item()), A, program, meta, sent
+
+    def e2e_step(i, host_in, host_out):
+        """Host tiles -> HBM -> factorise -> host tiles on every rank's share, all inside the timed region: the public
+        API with pinned host buffers (BigMatrix.put_block = async H2D, mirror_to_host = write-through D2H)."""
+        torch.cuda.synchronize()
+        dist.barrier(device_ids=[device.index])
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        A = BigMatrix(f"bench_e2e_{i}", shape=(n, n), shard_sizes=(b, b), device=device)
+        for (j, k) in sorted(host_in, key=lambda jk: (jk[1], jk[0])):
+            A.put_block(host_in[(j, k)], j, k)
+        program, meta = cholesky(A)
+        O = meta["outputs"][0]
+        O.mirror_to_host(host_out)
+        program.start()
+        job_runner.lambdapack_run(program, timeout=3600, streams=args.streams, consume_inputs=True)
+        O.wait_mirror()
+        e1.record()
+        e1.synchronize()
+        ok = program.program_status() == lp.PS.SUCCESS
+        ms = torch.tensor([e0.elapsed_time(e1) if ok else float("inf")], dtype=torch.float64, device=device)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        free_all(A, meta)
+        return float(ms.item())
 
     def residual(meta):
         """||(L L^T)_jk - A_jk|| / ||A_jk|| on the last diagonal tile, computed by its owner from gathered row tiles."""
@@ -508,6 +541,47 @@ def bench_main(args, metric, unit, workload):
                     "peak_source": "measured live on rank 0: max(DMMA issue probe %.2f, cuBLAS DGEMM %.2f) TFLOP/s per GPU" % (
                         peaks["dmma_pipe_tflops"], peaks["cublas_dgemm_tflops"]),
                     "whole_job_frac_of_aggregate_peak": value / (peak * grid.world)}
+    # ---- end to end with HOST buffers at this GPU count: every rank stages its own tiles in pinned memory
+    # (written after round 1's GPU budget was spent: opt-in until it has run on hardware once — a failure on one rank
+    # inside a collective step would cost the whole line)
+    e2e = {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+           "note": "host-buffer end-to-end is measured at N=1; NPW_B200_BENCH_E2E=1 enables the per-rank staging path here"}
+    if os.environ.get("NPW_B200_BENCH_E2E", "0") != "0":
+        host_in, host_out, ok = {}, {}, 1
+        try:
+            mine = [(j, k) for j in range(nb) for k in range(j + 1) if grid.owner_of_coords(j, k) == grid.rank]
+            if 2 * len(mine) * b * b * 8 > float(os.environ.get("NPW_B200_BENCH_E2E_MAX_GB", "96")) * 2 ** 30:
+                raise MemoryError("pinned staging for this rank's share exceeds NPW_B200_BENCH_E2E_MAX_GB")
+            for (j, k) in mine:
+                t = torch.empty(b, b, dtype=torch.float64, device=device)
+                kernels._gemm_into(t, None, X[j], X[k], False, True, 1.0, 0.0)
+                if j == k:
+                    kernels.add_diag(t, float(n))
+                h = torch.empty(b, b, dtype=torch.float64, pin_memory=True)
+                h.copy_(t)
+                host_in[(j, k)] = h
+                host_out[(j, k)] = torch.empty(b, b, dtype=torch.float64, pin_memory=True)
+                del t
+        except Exception as ex:  # pragma: no cover
+            ok = 0
+            e2e["error"] = repr(ex)
+        # every rank must agree before entering the collective timed steps
+        flag = torch.tensor([ok], dtype=torch.int64, device=device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            e2e_step("w", host_in, host_out)                                           # warm
+            ts = [e2e_step(f"t{r}", host_in, host_out) for r in range(max(1, min(args.steps, 2)))]
+            e_ms = float(np.mean(ts))
+            moved = torch.tensor([len(host_in) * b * b * 8], dtype=torch.int64, device=device)
+            dist.all_reduce(moved, op=dist.ReduceOp.SUM)
+            if np.isfinite(e_ms):
+                e2e = {"value": (n ** 3 / 3.0) / (e_ms * 1e-3) * 1e-12, "unit": unit, "h2d_bytes_per_step": int(moved.item()),
+                       "d2h_bytes_per_step": int(moved.item()), "ms_per_step": e_ms,
+                       "what": "per rank: pinned host lower tiles -> BigMatrix.put_block (async H2D) -> cholesky() -> "
+                               "lambdapack_run -> factor tiles written through to pinned host (D2H) -> wait; max over ranks"}
+        elif "error" not in e2e:
+            e2e["error"] = "another rank could not stage its host buffers"
+        del host_in, host_out
     if grid.rank == 0:
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": grid.world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
@@ -517,10 +591,10 @@ def bench_main(args, metric, unit, workload):
                            "tile_tasks": nb * (nb + 1) * (nb + 2) // 6, "streams": args.streams,
                            "l2": "inputs larger than L2; every step regenerates its input",
                            "nvlink_bytes_per_step": int(sent_t.item()), "residual_LLt_minus_A": resid,
+                           "plan_s": plan_s[0],
                            "algorithmic_flops_per_step": n ** 3 / 3.0},
                 "roofline": roofline, "cpu_baseline": None,
-                "e2e": {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                        "note": "host-buffer end-to-end is measured at N=1 only"},
+                "e2e": e2e,
                 "gpu_launches": launches_tot, "clocks": clocks}
         print(json.dumps(line), flush=True)
     dist.barrier(device_ids=[device.index])
