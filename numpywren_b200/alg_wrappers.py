@@ -10,7 +10,7 @@ import numpy as np
 
 from . import config as npw_config
 from . import lambdapack as lp
-from .algs import BDFAC, CHOLESKY, GEMM, QR, TSQR
+from .algs import BDFAC, CHOLESKY, GEMM, GEMM_ACC, QR, TSQR
 from .compiler import lpcompile_for_execution
 from .matrix import BigMatrix
 from .matrix_utils import constant_zeros, constant_zeros_ext
@@ -101,6 +101,26 @@ def gemm(A, B):
     c_time = time.time() - t
     program = lp.LambdaPackProgram(p1, config=npw_config.default())
     return program, {"outputs": [C_sharded], "intermediates": [Temp], "compile_time": c_time}
+
+
+def gemm_kloop(A, B, out_key=None):
+    """Tiled A @ B with the legacy binops.gemm schedule (owner of every output tile accumulates over the reduction index
+    in place) as a LambdaPACK program — the multi-GPU path of ``binops.gemm``.  Returns (program, meta) like ``gemm``."""
+    assert (A.shape[1] == B.shape[0])
+    assert (A.shard_sizes[1] == B.shard_sizes[0])
+    K = A.num_blocks(1)
+    out_key = out_key or "matmul_kloop_C({0},{1})".format(A.key, B.key)
+    Acc = BigMatrix("matmul_kloop_Acc({0},{1})".format(A.key, B.key), shape=(K + 1, A.shape[0], B.shape[1]),
+                    shard_sizes=(1, A.shard_sizes[0], B.shard_sizes[1]), bucket=A.bucket, write_header=True, safe=False,
+                    device=A.device)
+    C = BigMatrix(out_key, shape=(A.shape[0], B.shape[1]), shard_sizes=(A.shard_sizes[0], B.shard_sizes[1]),
+                  bucket=A.bucket, write_header=True, device=A.device)
+    t = time.time()
+    p0 = lpcompile_for_execution(GEMM_ACC, inputs=["A", "B"], outputs=["Out"])
+    p1 = p0(A, B, A.num_blocks(0), B.num_blocks(1), K, Acc, C)
+    c_time = time.time() - t
+    program = lp.LambdaPackProgram(p1, config=npw_config.default())
+    return program, {"outputs": [C], "intermediates": [Acc], "compile_time": c_time}
 
 
 def _loose(key, X, shape, shard_sizes, parent_fn=None, place_axis=None, tile_shape=None):

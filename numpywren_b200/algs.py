@@ -41,6 +41,20 @@ def GEMM(A: BigMatrix, B: BigMatrix, M: int, N: int, K: int, Temp: BigMatrix, Ou
             Out[i, j] = identity(Temp[i, j, 0, tree_depth])
 
 
+def GEMM_ACC(A: BigMatrix, B: BigMatrix, M: int, N: int, K: int, Acc: BigMatrix, Out: BigMatrix):
+    # the legacy binops.gemm schedule (binops.py:19-33: one task per output tile, serial accumulation over the reduction
+    # index) written as a LambdaPACK program: Acc[k, i, j] is output tile (i, j) after k partial products (SSA; the
+    # engine accumulates in place).  Not in the reference's algs.py — it exists so that binops.gemm runs on the DAG
+    # engine, i.e. across GPUs: the owner of C[i, j] computes it, A[i, k] / B[k, j] tiles travel along process rows /
+    # columns (SUMMA's communication pattern, derived from the DAG like every other transfer).
+    for i in range(0, M):
+        for j in range(0, N):
+            Acc[1, i, j] = gemm(A[i, 0], B[0, j])
+            for k in range(1, K):
+                Acc[k + 1, i, j] = gemm_acc(Acc[k, i, j], A[i, k], B[k, j])
+            Out[i, j] = identity(Acc[K, i, j])
+
+
 def TSQR(A: BigMatrix, Vs: BigMatrix, Ts: BigMatrix, Rs: BigMatrix, N: int):
     # leaf QR of every row block, then a binary tree of QRs of stacked R factors
     for j in range(0, N):

@@ -5,6 +5,10 @@ The reference maps one pywren task per output tile, each running a serial loop o
 owner-computes-over-C-tiles schedule is issued straight onto CUDA streams: one stream per output tile (round robin), the
 k-loop accumulates in place through the GEMM core (``C = A.B + C``), tiles are read by reference from HBM.
 ``pwex`` (the pywren executor) is accepted and ignored: there is no remote fan-out on a single box.
+
+On several GPUs (one process per GPU, ``parallel.init_from_env``) the same schedule runs as the LambdaPACK program
+``algs.GEMM_ACC`` on the DAG engine: the owner of C[i, j] accumulates it, and the engine's transfer plan moves A[i, k]
+along the process row and B[k, j] along the process column over NVLink — SUMMA's communication, derived from the DAG.
 """
 from __future__ import annotations
 
@@ -45,6 +49,10 @@ def gemm(pwex, X, Y, out_bucket=None, tasks_per_job=1, local=False, dtype=np.flo
     if gemm_impl != 0:
         raise Exception("GEMM IMPL > 0 only supported for standalone mode pywren")
     root_key = generate_key_name_binop(X, Y, "gemm")
+    from . import parallel
+    grid = parallel.current_grid()
+    if grid is not None and grid.world > 1:
+        return _gemm_distributed(X, Y, root_key, streams)
     XY = BigMatrix(root_key, shape=(X.shape[0], Y.shape[1]), bucket=out_bucket,
                    shard_sizes=[X.shard_sizes[0], Y.shard_sizes[1]], dtype=dtype, write_header=True, device=X.device)
     todo = list(XY.block_idxs) if overwrite else list(XY.block_idxs_not_exist)
@@ -72,3 +80,18 @@ def gemm(pwex, X, Y, out_bucket=None, tasks_per_job=1, local=False, dtype=np.flo
             done.record(s)
             XY._entry["ready"][(i, j)] = done       # readers on other streams wait for this tile's last update
     return XY
+
+
+def _gemm_distributed(X, Y, root_key, streams):
+    """binops.gemm across GPUs: compile algs.GEMM_ACC for (X, Y), run it to completion on the engine, return C."""
+    from . import job_runner
+    from . import lambdapack as lp
+    from .alg_wrappers import gemm_kloop
+    program, meta = gemm_kloop(X, Y, out_key=root_key)
+    program.start()
+    job_runner.lambdapack_run(program, timeout=3600, streams=max(streams, 8))
+    if program.program_status() != lp.PS.SUCCESS:
+        raise Exception("binops.gemm: program ended with status {0}".format(program.program_status()))
+    for m in meta["intermediates"]:
+        m.free()
+    return meta["outputs"][0]

@@ -290,6 +290,10 @@ class TileEngine:
                 out = args[1] if can_overwrite(1) else None
                 consumed = 1 if out is not None else None
                 results = kernels.trsm_with_inverse(args[0], args[1], self.invdiag.get(keys[0]), out=out)
+            elif fn is kernels.gemm_acc and len(args) == 3:
+                out = args[0] if can_overwrite(0) else None
+                consumed = 0 if out is not None else None
+                results = kernels.gemm_acc(args[0], args[1], args[2], out=out)
             elif fn is kernels.chol and len(args) == 1:
                 out = args[0] if can_overwrite(0) else None
                 consumed = 0 if out is not None else None

@@ -24,7 +24,7 @@ from . import _capi
 __all__ = [
     "add_matrices", "syrk", "chol", "trsm", "gemm", "mul", "identity", "qr_factor",
     "qr_factor_triangular", "qr_leaf", "qr_trailing_update", "lq_factor", "lq_leaf", "lq_trailing_update",
-    "chol_async", "trsm_with_inverse", "transpose", "add_diag", "fill_random",
+    "gemm_acc", "chol_async", "trsm_with_inverse", "transpose", "add_diag", "fill_random",
 ]
 
 
@@ -291,6 +291,30 @@ def _gemm_accumulate(acc, A, B):
     if not b_t and min(acc.shape) >= 256:
         return _gemm_into(acc, acc, A, transpose(B), False, True, 1.0, 1.0)
     return _gemm_into(acc, acc, A, B, False, False, 1.0, 1.0)
+
+
+def gemm_acc(c, a, b, *args, out=None, **kwargs):
+    """c + a.dot(b): one step of the serial reduction loop of the legacy binops GEMM
+    (``XY_block += X.get_block(i, r).dot(Y.get_block(r, j))``, binops.py:19-33) as a tile kernel, so that the same
+    owner-computes / K-loop schedule can run as a LambdaPACK program (algs.GEMM_ACC) on the DAG engine and across
+    GPUs.  ``out`` (scheduler use) may be ``c`` itself: in-place accumulation."""
+    _check_tile(c, "c")
+    _check_tile(a, "a")
+    _check_tile(b, "b")
+    if a.shape[1] != b.shape[0]:
+        raise ValueError(f"shapes {tuple(a.shape)} and {tuple(b.shape)} not aligned: {a.shape[1]} (dim 1) != {b.shape[0]} (dim 0)")
+    out = _out_tile(out, (a.shape[0], b.shape[1]), c.device, "out")
+    if tuple(c.shape) != tuple(out.shape):
+        raise ValueError(f"operands could not be broadcast together with shapes {tuple(c.shape)} {tuple(out.shape)}")
+    return _gemm_any(out, c, a, b, False, False, 1.0, 1.0)
+
+
+def _gemm_acc_flops(c, a, b):
+    m, n = a.shape
+    return 2 * m * n * b.shape[1] + m * b.shape[1]
+
+
+gemm_acc.flops = _gemm_acc_flops
 
 
 def _gemm_flops(A, B):

@@ -62,9 +62,19 @@ def main():
     fac = orc.bdfac_assemble(Rq, L, n, b, get=lambda m, *idx: gather_tile(m, idx, grid))
     serr = np.abs(np.linalg.svd(fac, compute_uv=False) - np.linalg.svd(X, compute_uv=False)).max()
     assert serr < 1e-9, serr
+    # legacy binops.gemm across GPUs (algs.GEMM_ACC on the engine; A / B tiles travel, C tiles accumulate in place)
+    from numpywren_b200 import binops
+    rs = np.random.RandomState(5)
+    ga, gb = rs.randn(768, 640), rs.randn(640, 512)
+    GA = BigMatrix("mgq_GA", shape=ga.shape, shard_sizes=(128, 128)); shard_matrix(GA, ga)
+    GB = BigMatrix("mgq_GB", shape=gb.shape, shard_sizes=(128, 128)); shard_matrix(GB, gb)
+    XY = binops.gemm(None, GA, GB)
+    C = XY.numpy()                                  # collective gather
+    gerr = np.linalg.norm(C - ga @ gb) / np.linalg.norm(ga @ gb)
+    assert gerr < 1e-13, gerr
     dist.barrier()
     if grid.rank == 0:
-        print("MULTI_GPU_QR_OK", grid.world, f"svd err {serr:.2e}")
+        print("MULTI_GPU_QR_OK", grid.world, f"svd err {serr:.2e} gemm err {gerr:.2e}")
     dist.destroy_process_group()
 
 

@@ -118,6 +118,30 @@ def main():
             for key, m, idx, src, dst in lst:
                 assert int(np.prod(parallel._tile_shape(m, idx))) in (16, 32), (which, m.key, idx)
 
+    # ---- binops.gemm across ranks = algs.GEMM_ACC: C tiles never move, only A / B (program inputs) are shipped,
+    #      each at most once per destination, and only along its process row (A) or process column (B)
+    Ag = BigMatrix("dist_gA", shape=(24, 24), shard_sizes=(4, 4), device="cpu")
+    Bg = BigMatrix("dist_gB", shape=(24, 24), shard_sizes=(4, 4), device="cpu")
+    program, meta = alg_wrappers.gemm_kloop(Ag, Bg)
+    gp = parallel.TransferPlan(program.program, grid)
+    assert not gp.after_node                                               # no produced tile crosses ranks
+    seen = set()
+    for lst in gp.before_node.values():
+        for key, m, idx, src, dst in lst:
+            assert m is Ag or m is Bg
+            assert (key, dst) not in seen
+            seen.add((key, dst))
+    for n in program.program.nodes:
+        if n.call.compute_name == "gemm_acc":
+            assert grid.owner(*n.reads[0]) == gp.exec_rank[n.nid] == grid.owner(*n.writes[0])
+    gs = [None] * world
+    dist.all_gather_object(gs, gp.describe(rank))
+    for a in range(world):
+        for b in range(world):
+            if a != b:
+                assert [k for (op, k, peer) in gs[a] if op == "send" and peer == b] == \
+                    [k for (op, k, peer) in gs[b] if op == "recv" and peer == a], ("gemm", a, b)
+
     # ---- failure agreement helper
     assert parallel.allreduce_max_int(rank * 3, torch.device("cpu")) == (world - 1) * 3
     dist.barrier()

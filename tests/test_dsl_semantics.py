@@ -51,7 +51,7 @@ def native_trace(fn, arg_names, args):
     ns = {"ceiling": lambda x: int(math.ceil(round(x, 9))), "floor": lambda x: int(math.floor(round(x, 9))),
           "log": math.log, "BigMatrix": BigMatrix}
     for k in ("chol", "trsm", "syrk", "gemm", "add_matrices", "identity", "qr_factor", "qr_factor_triangular", "qr_leaf",
-              "qr_trailing_update", "lq_factor", "lq_leaf", "lq_trailing_update"):
+              "qr_trailing_update", "lq_factor", "lq_leaf", "lq_trailing_update", "gemm_acc"):
         ns[k] = kernel(k)
     src = textwrap.dedent(inspect.getsource(fn))
     # tuple targets "A[..], B[..], C[..] = f(...)" assign the same call record to each target
@@ -77,6 +77,7 @@ CASES = [
     ("CHOLESKY", lambda n: (dummy(2), dummy(2), dummy(3), n, 0), [1, 2, 3, 5, 9, 16]),
     ("CHOLESKY", lambda n: (dummy(2), dummy(2), dummy(3), n, 2), [4, 7]),
     ("GEMM", lambda n: (dummy(2), dummy(2), n, n + 1, max(1, n - 1), dummy(4), dummy(2)), [1, 2, 3, 4, 5, 6, 17]),
+    ("GEMM_ACC", lambda n: (dummy(2), dummy(2), n, n + 1, max(1, n - 1), dummy(3), dummy(2)), [1, 2, 3, 5]),
     ("TSQR", lambda n: (dummy(2), dummy(2), dummy(2), dummy(2), n), [1, 2, 4, 8, 16, 32, 64]),
     ("QR", lambda n: (dummy(2), dummy(3), dummy(3), dummy(3), dummy(4), n, 0), [1, 2, 3, 4, 5, 8, 11]),
     ("BDFAC", lambda n: (dummy(2), dummy(3), dummy(3), dummy(4), dummy(3), dummy(3), dummy(3), dummy(4), dummy(3), n, 0),

@@ -240,3 +240,30 @@ def test_gemm_program_with_reclaimed_temporaries(unique_key, cuda_device):
     assert program._engine.freed_tiles > 0 and len(meta["intermediates"][0]._blocks_store) == 0
     for m in meta["outputs"] + meta["intermediates"] + [A, B]:
         m.free()
+
+
+@pytest.mark.parametrize("shape,tile", [((300, 260, 200), 128), ((1024, 1024, 1024), 256)])
+def test_gemm_kloop_program(unique_key, cuda_device, shape, tile):
+    """algs.GEMM_ACC on the engine (in-place accumulation of every output tile): the multi-GPU path of binops.gemm,
+    here on one GPU, against the oracle's restatement of the legacy schedule."""
+    m, k, n = shape
+    rs = np.random.RandomState(m + k + n)
+    a, b = rs.randn(m, k), rs.randn(k, n)
+    A = _bigmatrix(unique_key("gkA"), a, tile)
+    B = _bigmatrix(unique_key("gkB"), b, tile)
+    program, meta = alg_wrappers.gemm_kloop(A, B)
+    for mm in meta["outputs"] + meta["intermediates"]:
+        mm.free()
+    run(program)
+    C = meta["outputs"][0].numpy()
+    Ao = orc.OracleBigMatrix("A", a.shape, (tile, tile)); orc.shard_matrix(Ao, a)
+    Bo = orc.OracleBigMatrix("B", b.shape, (tile, tile)); orc.shard_matrix(Bo, b)
+    ref = orc.binops_gemm(Ao, Bo).numpy()
+    assert np.linalg.norm(C - ref) / np.linalg.norm(ref) < 1e-13
+    # every partial sum was accumulated in place: only the final version of each output tile is left in Acc
+    # (identity passes that very tensor on to Out)
+    Acc, Out = meta["intermediates"][0], meta["outputs"][0]
+    assert len(Acc._blocks_store) == len(Out._blocks_store) == len(Out.block_idxs)
+    assert np.array_equal(A.numpy(), a) and np.array_equal(B.numpy(), b)
+    for mm in meta["outputs"] + meta["intermediates"] + [A, B]:
+        mm.free()

@@ -176,3 +176,28 @@ def test_bdfac_program_householder_semantics_meets_reference_test(host, unique_k
     L, R = meta["outputs"]
     fac = orc.bdfac_assemble(R, L, n, b, get=lambda m, *idx: m.get_block(*idx).numpy())
     close(np.linalg.svd(fac, compute_uv=False), np.linalg.svd(X, compute_uv=False), 1e-10)
+
+
+def test_gemm_kloop_program_matches_the_legacy_binops_schedule(host, unique_key):
+    """algs.GEMM_ACC (the multi-GPU path of binops.gemm) through the host test double: same result as the oracle's
+    restatement of binops._gemm_remote_0 (serial accumulation over the reduction index), ragged tiles included."""
+    rs = np.random.RandomState(12)
+    a, b = rs.randn(300, 260), rs.randn(260, 200)
+    A = _bigmatrix(unique_key("gkA"), a, 128)
+    B = _bigmatrix(unique_key("gkB"), b, 128)
+    program, meta = alg_wrappers.gemm_kloop(A, B)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    cp = program.program
+    assert len(cp.nodes) == 3 * 2 * (3 + 1)            # per output tile: 1 gemm + (K-1) gemm_acc + 1 identity
+    for n in cp.nodes:                                   # every partial sum has one reader: in-place accumulation is legal
+        if n.call.compute_name in ("gemm", "gemm_acc"):
+            assert cp.num_readers(*n.writes[0]) == 1
+    _hostlib.run_in_program_order(program)
+    C = meta["outputs"][0].numpy()
+    Ao = orc.OracleBigMatrix("A", a.shape, (128, 128)); orc.shard_matrix(Ao, a)
+    Bo = orc.OracleBigMatrix("B", b.shape, (128, 128)); orc.shard_matrix(Bo, b)
+    close(C, orc.binops_gemm(Ao, Bo).numpy(), 1e-12)
+    close(C, a @ b, 1e-12)
+    # large tiles go to the DMMA core in NT form after the transpose kernel re-lays B out; accumulation aliases C0 = C
+    assert any(c[0] == "copy2d" and c[3] == 1 for c in host.calls)
