@@ -39,7 +39,7 @@ class ExpandedNode:
     __slots__ = ("nid", "expr_idx", "var_values", "call", "reads", "scalars", "arg_layout", "writes", "children",
                  "parents", "key")
 
-    def __init__(self, nid, expr_idx, var_values, call):
+    def __init__(self, nid, expr_idx, var_values, call, key=None):
         self.nid = nid
         self.expr_idx = expr_idx
         self.var_values = var_values
@@ -50,7 +50,7 @@ class ExpandedNode:
         self.writes: List[Tuple[Any, Tuple[int, ...]]] = []
         self.children: List[int] = []
         self.parents: List[int] = []
-        self.key = (expr_idx, _freeze(var_values))
+        self.key = key if key is not None else (expr_idx, _freeze(var_values))
 
     @property
     def ref(self) -> Node:
@@ -164,7 +164,66 @@ class CompiledLambdaPackProgram:
         walk(self.fdef.body, dict(ints), {})
         return out
 
+    def _expand_native(self) -> bool:
+        """Expansion by libnpw_dag (csrc/npw_dag.cpp).  Returns False when the Python expander below must run: library
+        not built, program outside the native subset, or an error for which Python raises its own exception."""
+        from . import _dag_native
+        t0 = time.time()
+        arr = _dag_native.expand(self)
+        if arr is None:
+            return False
+        names, mats = arr["slot_names"], arr["matrices"]
+        nt = arr["n_tiles"]
+        tio, tix, tm = arr["tile_idx_off"].tolist(), arr["tile_idx"].tolist(), arr["tile_matrix"].tolist()
+        from .matrix import BigMatrix
+        tiles = [(mats[tm[t]], tuple(tix[tio[t]:tio[t + 1]])) for t in range(nt)]
+        # _tile_key of a plain BigMatrix is (bucket, key, idx): skip the per-tile method calls for those
+        plain = [type(m) is BigMatrix for m in mats]
+        head = [(getattr(m, "bucket", None), getattr(m, "key", id(m))) for m in mats]
+        keys = [head[tm[t]] + (tiles[t][1],) if plain[tm[t]] else _tile_key(*tiles[t]) for t in range(nt)]
+        expr = arr["node_expr"].tolist()
+        vo, vs, vv = arr["var_off"].tolist(), arr["var_slot"].tolist(), arr["var_val"].tolist()
+        ro, rt = arr["read_off"].tolist(), arr["read_tile"].tolist()
+        wo, wt = arr["write_off"].tolist(), arr["write_tile"].tolist()
+        co, cn = arr["child_off"].tolist(), arr["child"].tolist()
+        po, pn = arr["parent_off"].tolist(), arr["parent"].tolist()
+        nodes: List[ExpandedNode] = []
+        readers: Dict[Any, List[int]] = {}
+        order_of: Dict[int, List[int]] = {}      # per remote call: positions of its loop variables sorted by name
+        for nid in range(arr["n_nodes"]):
+            e = expr[nid]
+            call = self.remote_calls[e]
+            lo, hi = vo[nid], vo[nid + 1]
+            ent = order_of.get(e)
+            if ent is None:
+                vnames = [names[vs[a]] for a in range(lo, hi)]
+                order = sorted(range(hi - lo), key=lambda a: vnames[a])
+                ent = order_of[e] = (vnames, order, [vnames[a] for a in order])
+            vnames, order, snames = ent
+            vals = vv[lo:hi]
+            key = (e, tuple(zip(snames, [vals[a] for a in order])))
+            node = ExpandedNode(nid, e, dict(zip(vnames, vals)), call, key)
+            node.reads = [tiles[t] for t in rt[ro[nid]:ro[nid + 1]]]
+            node.arg_layout = [("read", a) for a in range(len(node.reads))]
+            node.writes = [tiles[t] for t in wt[wo[nid]:wo[nid + 1]]]
+            node.children = cn[co[nid]:co[nid + 1]]
+            node.parents = pn[po[nid]:po[nid + 1]]
+            for t in rt[ro[nid]:ro[nid + 1]]:
+                readers.setdefault(keys[t], []).append(nid)
+            nodes.append(node)
+        tw = arr["tile_writer"].tolist()
+        self._nodes = nodes
+        self._by_key = {n.key: n.nid for n in nodes}
+        self._writer = {keys[t]: tw[t] for t in range(nt) if tw[t] >= 0}
+        self._readers = readers
+        self.expand_time = time.time() - t0
+        self.expanded_by = "native"
+        return True
+
     def _expand(self):
+        if self._expand_native():
+            return
+        self.expanded_by = "python"
         t0 = time.time()
         nodes: List[ExpandedNode] = []
         call_idx = {id(c): i for i, c in self.remote_calls.items()}

@@ -1,0 +1,157 @@
+"""libnpw_dag.so (csrc/npw_dag.cpp, include/npw_dag.h) against the Python expander it mirrors: identical nodes, tiles
+and edges for every program in algs.py over a sweep of sizes, identical expression semantics (Python's int/float rules,
+floor division and modulo signs, the exact ceiling(log(a)/log(b))), and a clean fallback where it does not apply."""
+import math
+import os
+
+import pytest
+
+from numpywren_b200 import _dag_native, algs, compiler, frontend
+from numpywren_b200.matrix import BigMatrix
+
+_n = [0]
+
+
+def dummy(nd):
+    _n[0] += 1
+    return BigMatrix("nd_%d" % _n[0], shape=tuple([4096] * nd), shard_sizes=tuple([1] * nd), device="cpu")
+
+
+def both(fn, args, namespace=None):
+    """Expand the same bound program with the native library and with the Python expander."""
+    if _dag_native.load() is None:
+        pytest.skip("libnpw_dag.so is not built")
+    p_nat = compiler.lpcompile(fn, namespace)(*args)
+    p_nat.nodes
+    assert p_nat.expanded_by == "native"
+    p_py = compiler.lpcompile(fn, namespace)(*args)
+    os.environ["NPW_B200_NATIVE_DAG"] = "0"
+    saved = (_dag_native._lib, _dag_native._load_failed)
+    _dag_native._lib, _dag_native._load_failed = None, False
+    try:
+        p_py.nodes
+    finally:
+        os.environ.pop("NPW_B200_NATIVE_DAG")
+        _dag_native._lib, _dag_native._load_failed = saved
+    assert p_py.expanded_by == "python"
+    return p_nat, p_py
+
+
+def same(p_nat, p_py):
+    assert len(p_nat.nodes) == len(p_py.nodes)
+    for a, b in zip(p_nat.nodes, p_py.nodes):
+        assert (a.nid, a.expr_idx, a.var_values, list(a.var_values)) == (b.nid, b.expr_idx, b.var_values, list(b.var_values))
+        assert [(id(m), idx) for m, idx in a.reads] == [(id(m), idx) for m, idx in b.reads]
+        assert [(id(m), idx) for m, idx in a.writes] == [(id(m), idx) for m, idx in b.writes]
+        assert a.arg_layout == b.arg_layout and a.children == b.children and a.parents == b.parents and a.key == b.key
+    assert p_nat._writer == p_py._writer and p_nat._readers == p_py._readers
+
+
+CASES = [
+    ("CHOLESKY", lambda n: (dummy(2), dummy(2), dummy(3), n, 0), [1, 2, 5, 16]),
+    ("CHOLESKY", lambda n: (dummy(2), dummy(2), dummy(3), n, 2), [4, 7]),
+    ("GEMM", lambda n: (dummy(2), dummy(2), n, n + 1, max(1, n - 1), dummy(4), dummy(2)), [1, 2, 5, 17]),
+    ("GEMM_ACC", lambda n: (dummy(2), dummy(2), n, n + 1, max(1, n - 1), dummy(3), dummy(2)), [1, 3, 6]),
+    ("TSQR", lambda n: (dummy(2), dummy(2), dummy(2), dummy(2), n), [1, 2, 3, 8, 33, 64]),
+    ("QR", lambda n: (dummy(2), dummy(3), dummy(3), dummy(3), dummy(4), n, 0), [1, 2, 3, 5, 8, 11]),
+    ("BDFAC", lambda n: (dummy(2), dummy(3), dummy(3), dummy(4), dummy(3), dummy(3), dummy(3), dummy(4), dummy(3), n, 0), [2, 3, 5, 9]),
+    ("BDFAC", lambda n: (dummy(2), dummy(3), dummy(3), dummy(4), dummy(3), dummy(3), dummy(3), dummy(4), dummy(3), n, 2), [4, 6]),
+    ("SimpleTestLinear", lambda n: (dummy(2), dummy(2), n), [1, 6]),
+    ("SimpleTestNonLinear", lambda n: (dummy(3), dummy(1), n), [1, 2, 8, 16]),
+]
+
+
+@pytest.mark.parametrize("prog,make,sizes", CASES)
+def test_native_expansion_equals_python_expansion(prog, make, sizes):
+    for n in sizes:
+        same(*both(getattr(algs, prog), make(n)))
+
+
+def test_benchmark_dag_is_expanded_natively_and_faster():
+    if _dag_native.load() is None:
+        pytest.skip("libnpw_dag.so is not built")
+    p_nat, p_py = both(algs.CHOLESKY, (dummy(2), dummy(2), dummy(3), 32, 0))
+    same(p_nat, p_py)
+    assert len(p_nat.nodes) == 5984
+    assert p_nat.expand_time < p_py.expand_time
+
+
+EXPR_PROGRAM = '''
+def P(A: BigMatrix, B: BigMatrix, N: int, x: float):
+    for i in range(-3, N):
+        q = (7 * i - 5) // 3
+        r = (7 * i - 5) % -4
+        for j in range(N, i, -2):
+            t = ceiling(log(j + 8) / log(2)) + floor(x * j) + (i ** 2) // 2
+            if (i < j and not (j % 3 == 0)) or i == 1:
+                B[i + 4, j, q + 20, r + 10, t] = identity(A[i + 4, j, 2 ** (j % 5), (j + 6) / 2 * 2])
+            else:
+                B[i + 4, j, 0, 0, t + ceiling(j / 3)] = identity(A[i + 4, j, 0, floor(log(j + 1) / log(3))])
+'''
+
+
+@pytest.mark.parametrize("N,x", [(1, 0.5), (6, 1.75), (9, -2.25)])
+def test_expression_semantics_follow_python(N, x):
+    """Negative operands of // and %, negative range steps, true division feeding an index, ** , and / or / not, exact
+    logs: the native evaluator and Python's eval must agree on every tile index."""
+    same(*both(EXPR_PROGRAM, (dummy(4), dummy(5), N, x)))
+
+
+def test_exact_log_ratio_for_integer_powers():
+    src = '''
+def P(A: BigMatrix, B: BigMatrix, N: int):
+    for i in range(1, N):
+        B[i, ceiling(log(i) / log(2)), ceiling(log(3 ** i) / log(3)), floor(log(10 ** i) / log(10))] = identity(A[i, 0, 0, 0])
+'''
+    p_nat, p_py = both(src, (dummy(4), dummy(4), 19))
+    same(p_nat, p_py)
+    for n in p_nat.nodes:
+        i = n.var_values["i"]
+        assert n.writes[0][1] == (i, max(0, (i - 1).bit_length()), i, i)
+        assert n.writes[0][1][1] == int(math.ceil(round(math.log(i) / math.log(2), 9)))
+
+
+def test_fallback_for_programs_outside_the_native_subset(unique_key):
+    if _dag_native.load() is None:
+        pytest.skip("libnpw_dag.so is not built")
+    # a scalar kernel argument is evaluated in Python
+    src = '''
+def P(A: BigMatrix, B: BigMatrix, N: int):
+    for i in range(N):
+        B[i] = mul(A[i], 2.5)
+'''
+    p = compiler.lpcompile(src)(dummy(1), dummy(1), 3)
+    assert len(p.nodes) == 3 and p.expanded_by == "python" and p.nodes[0].scalars == [2.5]
+    # a view argument remaps block indices in Python
+    X = BigMatrix(unique_key("v"), shape=(8, 8), shard_sizes=(2, 2), device="cpu")
+    p = compiler.lpcompile(algs.SimpleTestLinear)(X.T, dummy(2), 3)
+    assert len(p.nodes) > 0 and p.expanded_by == "python"
+    # errors keep their Python exception: a non-SSA program, a zero range step
+    bad = '''
+def P(A: BigMatrix, B: BigMatrix, N: int):
+    for i in range(N):
+        B[0] = identity(A[i])
+'''
+    with pytest.raises(Exception, match="SSA"):
+        compiler.lpcompile(bad)(dummy(1), dummy(1), 2).nodes
+    zero = '''
+def P(A: BigMatrix, B: BigMatrix, N: int):
+    for i in range(0, N, N - N):
+        B[i] = identity(A[i])
+'''
+    with pytest.raises(Exception, match="step"):
+        compiler.lpcompile(zero)(dummy(1), dummy(1), 2).nodes
+
+
+def test_header_and_library_agree():
+    if _dag_native.load() is None:
+        pytest.skip("libnpw_dag.so is not built")
+    import ctypes
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    hdr = open(os.path.join(root, "include", "npw_dag.h")).read()
+    names = set(re.findall(r"\b(npw_dag_[a-z_]+)\s*\(", hdr))
+    assert names == {"npw_dag_expand", "npw_dag_arrays", "npw_dag_free", "npw_dag_abi_version"}
+    lib = ctypes.CDLL(_dag_native._LIB_PATH)
+    for n in names:
+        getattr(lib, n)
