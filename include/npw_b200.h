@@ -181,6 +181,27 @@ int npw_tpqrt_f64(double* V2, int64_t ldv, double* T, int64_t ldt,
                   const double* R0, int64_t ld0, const double* R1, int64_t ld1,
                   int64_t n, void* work, npw_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * EXPERIMENTAL (never run on hardware in round 1; not used by the default path):
+ * kernels.syrk (kernels.py:212-215) with the product X Y^T emulated on the int8
+ * tensor cores (tcgen05.mma kind::i8) — DESIGN.md §8, tools/ozaki_prototype.py.
+ *   npw_split_i8_f64: X (rows x k, fp64) -> `ndigits` signed int8 digit planes
+ *     (digits[p][row][col], k contiguous, 6 + 7 + 7 ... bits) and per-row exponents,
+ *     X = diag(2^e) sum_p 2^-(6+7p) X_p exactly up to the last digit.
+ *     digits: npw_i8_digits_bytes(rows, k, ndigits) bytes; exponents: rows int32.
+ *   npw_syrk_i8emu_f64: C = S - X Y^T from the digits of X (m x k) and Y (n x k);
+ *     m % 128 == 0, n % 64 == 0, k % 128 == 0, 1 <= ndigits <= 8; C may alias S;
+ *     lower_only skips the 128 x 64 tiles strictly above the diagonal.
+ * ---------------------------------------------------------------------- */
+size_t npw_i8_digits_bytes(int64_t rows, int64_t k, int ndigits);
+int npw_split_i8_f64(int8_t* digits, int32_t* exponents, const double* X, int64_t ldx,
+                     int64_t rows, int64_t k, int ndigits, npw_stream_t stream);
+int npw_syrk_i8emu_f64(double* C, int64_t ldc, const double* S, int64_t lds,
+                       const int8_t* xdigits, const int32_t* xexp,
+                       const int8_t* ydigits, const int32_t* yexp,
+                       int64_t m, int64_t n, int64_t k, int ndigits, int lower_only,
+                       npw_stream_t stream);
+
 /* Device-side synthetic tile generator used by bench/tests (not a reference
  * op): counter-based uniform(-1,1) fill, reproducible from (seed, row, col). */
 int npw_fill_random_f64(double* A, int64_t lda, int64_t rows, int64_t cols,

@@ -54,6 +54,10 @@ _SIGNATURES = {
     "npw_tpqrt_work_bytes": (c_size_t, [c_int64]),
     "npw_tpqrt_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                               c_int64, c_void_p, c_void_p]),
+    "npw_i8_digits_bytes": (c_size_t, [c_int64, c_int64, c_int]),
+    "npw_split_i8_f64": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_void_p]),
+    "npw_syrk_i8emu_f64": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_int64, c_int64, c_int64, c_int, c_int, c_void_p]),
     "npw_fp64_pipe_probe_bytes": (c_size_t, [c_int]),
     "npw_fp64_pipe_probe": (c_int, [c_void_p, c_int, c_int, ctypes.POINTER(c_double), c_void_p]),
     "npw_fill_random_f64": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_uint64, c_int64, c_int64, c_void_p]),

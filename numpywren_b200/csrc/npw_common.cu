@@ -56,6 +56,26 @@ int make_tmap_f64(CUtensorMap* map, const double* base, int64_t rows, int64_t co
   return 0;
 }
 
+// 3-D int8 tensor map over `planes` digit planes of a row-major rows x k byte matrix (k contiguous):
+// box = 128 bytes of k x box_rows rows x 1 plane, 128-byte swizzle (the K-major SWIZZLE_128B operand layout of tcgen05.mma).
+int make_tmap_i8_3d(CUtensorMap* map, const int8_t* base, int64_t rows, int64_t k, int64_t planes, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return -1;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(planes)};
+  cuuint64_t gstride[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(k) * static_cast<cuuint64_t>(rows)};
+  cuuint32_t box[3] = {128u, box_rows, 1u};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<int8_t*>(base), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (int8 digits) failed: CUresult %d (base=%p rows=%lld k=%lld planes=%lld)", (int)r,
+              (const void*)base, (long long)rows, (long long)k, (long long)planes);
+    return -1;
+  }
+  return 0;
+}
+
 }  // namespace npw
 
 extern "C" {

@@ -420,6 +420,38 @@ def _gemm_any(out, c0, A, B, trans_a, trans_b, alpha, beta):
     return _gemm_into(out, c0, A, B, trans_a, trans_b, alpha, beta)
 
 
+# ----------------------------------------------------------------------------- EXPERIMENTAL: int8-tensor-core emulation
+def split_i8(x, digits=6):
+    """EXPERIMENTAL (never run on hardware in round 1).  fp64 tile -> (int8 digit planes [digits, rows, k],
+    int32 row exponents) for ``syrk_i8emu``: x = diag(2^e) sum_p 2^-(6+7p) x_p."""
+    x = _rowmajor(x, "x")
+    rows, k = x.shape
+    lib = _capi.load()
+    d = torch.empty((digits, rows, k), dtype=torch.int8, device=x.device)
+    e = torch.empty((rows,), dtype=torch.int32, device=x.device)
+    rc = lib.npw_split_i8_f64(d.data_ptr(), e.data_ptr(), x.data_ptr(), max(1, x.stride(0)), rows, k, int(digits), _stream())
+    _capi.check(rc, "npw_split_i8_f64")
+    return d, e
+
+
+def syrk_i8emu(s, xd, xe, yd, ye, out=None, lower=False):
+    """EXPERIMENTAL.  s - x.dot(y.T) from the int8 digits of x and y (``split_i8``): the product runs on the int8 tensor
+    cores (tcgen05.mma kind::i8) with exact int32 group sums, the combination in fp64."""
+    _check_tile(s, "s")
+    sm = _rowmajor(s, "s")
+    digits, m, k = xd.shape
+    n = yd.shape[1]
+    if yd.shape[0] != digits or yd.shape[2] != k:
+        raise ValueError(f"digit tensors do not match: {tuple(xd.shape)} vs {tuple(yd.shape)}")
+    out = _out_tile(out, (m, n), s.device, "out")
+    if tuple(sm.shape) != (m, n):
+        raise ValueError(f"operands could not be broadcast together with shapes {tuple(s.shape)} ({m},{n})")
+    rc = _capi.load().npw_syrk_i8emu_f64(out.data_ptr(), out.stride(0), sm.data_ptr(), sm.stride(0), xd.data_ptr(), xe.data_ptr(),
+                                         yd.data_ptr(), ye.data_ptr(), m, n, k, int(digits), int(bool(lower)), _stream())
+    _capi.check(rc, "npw_syrk_i8emu_f64")
+    return out
+
+
 # ----------------------------------------------------------------------------- helpers (not in the reference)
 def transpose(x):
     """Row-major copy of x.T (BigMatrixView transposed reads, matrix.py:643-661)."""

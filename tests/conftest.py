@@ -15,6 +15,8 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "gpu_experimental: kernels that have never run on hardware yet (NOT part of -m gpu; "
+                                       "run explicitly with -m gpu_experimental)")
 
 
 @pytest.fixture(scope="session")

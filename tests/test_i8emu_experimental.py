@@ -1,0 +1,68 @@
+"""EXPERIMENTAL kernels (csrc/npw_ozaki_i8.cu): fp64 syrk emulated on the int8 tensor cores.  Written after round 1's GPU
+budget was spent, so these tests have never run; they carry their own marker and are NOT selected by `-m gpu`:
+
+    NPW_B200_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_i8emu_experimental.py -m gpu_experimental -x -q
+
+Order matters when debugging: digits first (plain CUDA), then one 128 x 64 x 128 tile, then the benchmark tile."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from numpywren_b200 import kernels
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import ozaki_prototype as oz  # noqa: E402
+
+pytestmark = [pytest.mark.gpu_experimental,
+              pytest.mark.skipif(os.environ.get("NPW_B200_EXPERIMENTAL") != "1",
+                                 reason="never-run tcgen05 kernels: set NPW_B200_EXPERIMENTAL=1 (and wrap the run in `timeout`)")]
+
+
+def dev(a, device):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(device)
+
+
+@pytest.mark.parametrize("digits", [1, 6, 8])
+def test_split_i8_matches_the_prototype_bit_for_bit(cuda_device, digits):
+    rs = np.random.RandomState(digits)
+    x = rs.randn(256, 384) * np.exp(rs.uniform(-20, 20, size=256))[:, None]
+    x[3] = 0.0
+    x[5, 0] = 2.0 ** 10
+    d, e = kernels.split_i8(dev(x, cuda_device), digits)
+    dref, eref, _ = oz.split_rows(x, digits)
+    assert np.array_equal(e.cpu().numpy(), eref.astype(np.int32))
+    assert np.array_equal(d.cpu().numpy(), dref)
+
+
+@pytest.mark.parametrize("m,n,k,digits", [(128, 64, 128, 1), (128, 64, 128, 6), (128, 64, 512, 8), (256, 192, 1024, 6),
+                                          (4096, 4096, 4096, 6)])
+def test_syrk_i8emu_matches_the_prototype(cuda_device, m, n, k, digits):
+    rs = np.random.RandomState(m + n + k + digits)
+    x, y, s = rs.randn(m, k), rs.randn(n, k), rs.randn(m, n)
+    xd, xe = kernels.split_i8(dev(x, cuda_device), digits)
+    yd, ye = kernels.split_i8(dev(y, cuda_device), digits)
+    c = kernels.syrk_i8emu(dev(s, cuda_device), xd, xe, yd, ye).cpu().numpy()
+    if m <= 256:
+        ref = s - oz.ozaki_gemm_nt(x, y, digits)[0]           # same digits, same dropped pairs: agreement to rounding
+        assert np.abs(c - ref).max() <= 1e-13 * np.abs(ref).max()
+    exact = s - x @ y.T
+    tol = {1: 0.3, 6: 1e-10, 8: 1e-13}[digits]
+    assert np.linalg.norm(c - exact) / np.linalg.norm(exact) < tol
+
+
+def test_syrk_i8emu_in_place_and_lower_only(cuda_device):
+    rs = np.random.RandomState(1)
+    x, s = rs.randn(512, 256), rs.randn(512, 512)
+    xd, xe = kernels.split_i8(dev(x, cuda_device), 6)
+    st = dev(s, cuda_device)
+    out = kernels.syrk_i8emu(st, xd, xe, xd, xe, out=st, lower=True)
+    assert out.data_ptr() == st.data_ptr()
+    c = out.cpu().numpy()
+    exact = s - x @ x.T
+    i, j = np.indices(c.shape)
+    low = j // 64 * 64 <= i // 128 * 128 + 127              # 128 x 64 tiles touching the lower triangle are computed
+    assert np.abs(c[low] - exact[low]).max() < 1e-9
+    assert np.array_equal(c[~low], s[~low])                  # the others are left alone
