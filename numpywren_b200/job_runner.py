@@ -130,6 +130,13 @@ class TileEngine:
                            if n in self.compiled.scope}
         self._reads_left: Dict[Any, int] = {}
         self.freed_tiles = 0
+        # EXPERIMENTAL, off by default (NPW_B200_SYRK=i8emu): syrk products on the int8 tensor cores.
+        # The int8 digits of a panel tile are a per-tile by-product like invdiag: extracted once, reused by every syrk
+        # of the tile's block row / column, dropped after the last one.
+        self.syrk_mode = os.environ.get("NPW_B200_SYRK", "native")
+        self.i8_digits = int(os.environ.get("NPW_B200_I8_DIGITS", "6"))
+        self._digits: Dict[Any, Tuple[torch.Tensor, torch.Tensor, torch.cuda.Event]] = {}
+        self._digit_uses: Dict[Any, int] = {}
 
     # ------------------------------------------------------------------ priorities
     def priorities(self) -> List[int]:
@@ -285,7 +292,14 @@ class TileEngine:
                 # a diagonal tile S[i,j,j] = S - L_j L_j^T feeds only chol (lower triangle) or the next diagonal
                 # syrk: the CTA tiles strictly above the diagonal are skipped (half the flops of these tasks)
                 diag = self.skip_upper and keys[1] == keys[2] and self._only_feeds_lower_readers(node)
-                results = kernels.syrk(args[0], args[1], args[2], out=out, lower=diag)
+                if self.syrk_mode == "i8emu" and self._i8emu_ok(args):
+                    xd, xe = self._tile_digits(node, 1, args[1], keys[1], stream)
+                    yd, ye = self._tile_digits(node, 2, args[2], keys[2], stream)
+                    results = kernels.syrk_i8emu(args[0], xd, xe, yd, ye, out=out, lower=diag)
+                    self._release_digits(keys[1])
+                    self._release_digits(keys[2])
+                else:
+                    results = kernels.syrk(args[0], args[1], args[2], out=out, lower=diag)
             elif fn is kernels.trsm and len(args) == 2:
                 out = args[1] if can_overwrite(1) else None
                 consumed = 1 if out is not None else None
@@ -339,6 +353,45 @@ class TileEngine:
             prog.incr_read(lp._nbytes(m))
         for (m, _) in node.writes:
             prog.incr_write(lp._nbytes(m))
+
+    # ------------------------------------------------------------------ experimental int8 emulation plumbing
+    @staticmethod
+    def _i8emu_ok(args) -> bool:
+        s, x, y = args[0], args[1], args[2]
+        return (x.dim() == 2 and y.dim() == 2 and x.shape[0] % 128 == 0 and y.shape[0] % 64 == 0 and x.shape[1] % 128 == 0
+                and x.shape[1] == y.shape[1] and x.is_contiguous() and y.is_contiguous())
+
+    def _syrk_uses(self, key) -> int:
+        """How many syrk operand slots read this tile in the whole program (each needs the digits once)."""
+        n = self._digit_uses.get(key)
+        if n is None:
+            n = 0
+            for nid in self.compiled._readers.get(key, ()):
+                nd = self.compiled.nodes[nid]
+                if nd.call.compute is kernels.syrk and len(nd.reads) == 3:
+                    n += sum(1 for j in (1, 2) if _tile_key(*nd.reads[j]) == key)
+            self._digit_uses[key] = n
+        return n
+
+    def _tile_digits(self, node, j, tile, key, stream):
+        ent = self._digits.get(key)
+        if ent is None:
+            self._syrk_uses(key)
+            d, e = kernels.split_i8(tile, self.i8_digits)
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            ent = self._digits[key] = (d, e, ev, stream)
+        elif ent[3] is not stream:
+            stream.wait_event(ent[2])
+            ent[0].record_stream(stream)
+            ent[1].record_stream(stream)
+        return ent[0], ent[1]
+
+    def _release_digits(self, key):
+        left = self._digit_uses.get(key, 0) - 1
+        self._digit_uses[key] = left
+        if left <= 0:
+            self._digits.pop(key, None)
 
     def _release_dead_inputs(self, node, refs, keys, consumed):
         """Drop stored intermediates whose every reader has now been enqueued (stream order + record_stream keep the
