@@ -135,7 +135,7 @@ class TileEngine:
         # of the tile's block row / column, dropped after the last one.
         self.syrk_mode = os.environ.get("NPW_B200_SYRK", "native")
         self.i8_digits = int(os.environ.get("NPW_B200_I8_DIGITS", "6"))
-        self._digits: Dict[Any, Tuple[torch.Tensor, torch.Tensor, torch.cuda.Event]] = {}
+        self._digits: Dict[Any, Tuple[Any, ...]] = {}     # tile key -> (digits, exponents, ready event, stream)
         self._digit_uses: Dict[Any, int] = {}
 
     # ------------------------------------------------------------------ priorities
