@@ -15,8 +15,9 @@ timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpur
 for s in 5 6 8; do timeout 300 python tools/ozaki_lib_probe.py --size 4096 --digits $s 2>&1 | tail -1 | tee -a gpurun_out/ozaki_lib_probe.jsonl; done
 # 4b. the never-run tcgen05 int8 kernel, smallest case first, each under its own timeout (a hang must not cost the box)
 for t in "test_split_i8_matches_the_prototype_bit_for_bit" "test_syrk_i8emu_matches_the_prototype[128-64-128-1]" \
-         "test_syrk_i8emu_matches_the_prototype[128-64-128-6]" "test_syrk_i8emu_matches_the_prototype"; do
-  NPW_B200_EXPERIMENTAL=1 timeout 120 python -m pytest "tests/test_i8emu_experimental.py" -m gpu_experimental -x -q -k "$t" 2>&1 | tail -6 | tee -a gpurun_out/i8emu_experimental.log
+         "test_syrk_i8emu_matches_the_prototype[128-64-128-6]" "test_syrk_i8emu_matches_the_prototype" \
+         "test_syrk_i8emu_in_place_and_lower_only"; do
+  NPW_B200_EXPERIMENTAL=1 timeout 120 python -m pytest "tests/test_i8emu_experimental.py::$t" -m gpu_experimental -x -q 2>&1 | tail -6 | tee -a gpurun_out/i8emu_experimental.log
 done
 # 5. launch lists of the programs that have never been profiled: QR program, streaming kernels via the GEMM program
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/launches_qr.csv \
