@@ -13,10 +13,11 @@
 //   2. npw_syrk_i8emu_f64: C = S - diag(2^ex) (sum_d 2^-(12+7d) P_d) diag(2^ey),  P_d = sum_{p+q=d} X_p Y_q^T in int32
 //                         (exact: |P_d| <= k 2^12 (d+1) < 2^31 for k <= 65536 / (d+1)); pairs with p+q > s-1 are dropped.
 //
-// Kernel 2 (one CTA per 128 x 64 output tile, 6 warps):
-//   warp 0   TMA producer.  Per 128-byte k-block: the s digit tiles of Y (64 rows x 128 B each) into one of two Y
-//            buffers, then the s digit tiles of X (128 rows x 128 B) one by one into a ring of NX slots.
-//            SWIZZLE_128B, 3-D tensor maps (k, row, digit plane).
+// Kernel 2 (one CTA per 128 x 64 output tile, 7 warps):
+//   warp 6   TMA producer of Y: per 128-byte k-block the s digit tiles of Y (64 rows x 128 B each) into one of two
+//            Y buffers;  warp 0: TMA producer of X: the s digit tiles of X (128 rows x 128 B) one by one into a ring of
+//            NX slots.  Two independent producers, so that the prefetch of the next k-block's Y digits never queues
+//            behind an X slot that is still being read.  SWIZZLE_128B, 3-D tensor maps (k, row, digit plane).
 //   warp 1   MMA issuer (one elected lane).  For digit p of X and every q <= s-1-p:  4 x tcgen05.mma (K = 32 bytes)
 //            M = 128, N = 64, accumulating into TMEM columns [64 (p+q), 64 (p+q+1)) — all s group accumulators stay
 //            resident in TMEM (s x 64 <= 512 columns), so every operand byte is loaded once per k-block.
@@ -33,7 +34,7 @@ constexpr int OZ_BK = 128;            // int8 elements = bytes per k-block (one 
 constexpr int OZ_UK = 32;             // K of one kind::i8 MMA
 constexpr int OZ_NX = 4;              // X ring slots
 constexpr int OZ_MAXS = 8;            // 8 x 64 = 512 TMEM columns
-constexpr int OZ_THREADS = 192;
+constexpr int OZ_THREADS = 224;           // warps: 0 X producer, 1 MMA issuer, 2-5 epilogue, 6 Y producer
 constexpr int OZ_XTILE = OZ_BM * OZ_BK;   // 16 KB
 constexpr int OZ_YTILE = OZ_BN * OZ_BK;   // 8 KB
 
@@ -200,23 +201,29 @@ ozaki_syrk_i8_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_const
   const int kblocks = p.k / OZ_BK;
 
   if (warp == 0) {
-    // ------------------------------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------------------------------ TMA producer: X digits
     if (lane == 0) {
       tma_prefetch_desc(&tmX);
-      tma_prefetch_desc(&tmY);
       int xit = 0;
       for (int kb = 0; kb < kblocks; ++kb) {
-        const int yb = kb & 1;
-        mbar_wait(&y_empty[yb], ((kb >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&y_full[yb], static_cast<uint32_t>(s * OZ_YTILE));
-        for (int q = 0; q < s; ++q)
-          tma_load_3d(ybuf + (yb * s + q) * OZ_YTILE, &tmY, &y_full[yb], kb * OZ_BK, tile_n * OZ_BN, q);
         for (int pd = 0; pd < s; ++pd, ++xit) {
           const int slot = xit % OZ_NX;
           mbar_wait(&x_empty[slot], ((xit / OZ_NX) & 1) ^ 1);
           mbar_arrive_expect_tx(&x_full[slot], static_cast<uint32_t>(OZ_XTILE));
           tma_load_3d(xring + slot * OZ_XTILE, &tmX, &x_full[slot], kb * OZ_BK, tile_m * OZ_BM, pd);
         }
+      }
+    }
+  } else if (warp == 6) {
+    // ------------------------------------------------------------------------------------------ TMA producer: Y digits
+    if (lane == 0) {
+      tma_prefetch_desc(&tmY);
+      for (int kb = 0; kb < kblocks; ++kb) {
+        const int yb = kb & 1;
+        mbar_wait(&y_empty[yb], ((kb >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&y_full[yb], static_cast<uint32_t>(s * OZ_YTILE));
+        for (int q = 0; q < s; ++q)
+          tma_load_3d(ybuf + (yb * s + q) * OZ_YTILE, &tmY, &y_full[yb], kb * OZ_BK, tile_n * OZ_BN, q);
       }
     }
   } else if (warp == 1) {
