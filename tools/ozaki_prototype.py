@@ -22,8 +22,10 @@ def split_rows(A, s):
     """-> (digits [s, m, k] int8, exponents e [m], weights w [s]) with A ~= 2^e[:,None] * sum_p 2^-w[p] * digits[p]."""
     A = np.asarray(A, dtype=np.float64)
     amax = np.abs(A).max(axis=1)
-    e = np.where(amax > 0, np.ceil(np.log2(np.where(amax > 0, amax, 1.0))), 0.0)
-    # make sure |r| <= 1 even when amax is an exact power of two
+    # e = ceil(log2(amax)) computed exactly from the binary representation (frexp: amax = m 2^ex, m in [0.5, 1)) — the
+    # same rule as split_i8_kernel in csrc/npw_ozaki_i8.cu, so that the two can be compared bit for bit
+    m, ex = np.frexp(amax)
+    e = np.where(amax > 0, np.where(m == 0.5, ex - 1, ex), 0).astype(np.float64)
     r = A / np.exp2(e)[:, None]
     digits = np.zeros((s,) + A.shape, dtype=np.int8)
     w = np.zeros(s)
