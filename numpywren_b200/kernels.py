@@ -232,12 +232,28 @@ def trsm_with_inverse(x, y, invdiag=None, out=None):
 def trsm(x, y, lower=False, right=True, *args, **kwargs):
     """scipy.linalg.blas.dtrsm(1.0, x.T, y, lower=lower, side=int(right))  — kernels.py:254-257.
 
-    The DSL always calls it with the defaults (frontend.py:346 drops keyword arguments), i.e.
-    ``y @ inv(x).T`` with x lower-triangular; other flag combinations are not on the hot path.
+    The DSL always calls it with the defaults (frontend.py:346 drops keyword arguments): ``y @ inv(tril(x)).T``, which is
+    the one triangular solve libnpw_b200 implements (npw_trsm_rlt_f64).  The other three flag combinations are mapped
+    onto it by data movement only — transposes, and index reversal J (J U J is lower triangular when U is upper):
+      right, lower=True : y inv(triu(x)).T       = ((y J) inv(J triu(x) J).T) J
+      left,  lower=True : inv(triu(x)).T y       = (y.T inv(triu(x)).T... ) see below
+      left,  lower=False: inv(tril(x)).T y       = (y.T inv(tril(x)))^T  = ((y.T J) inv(J tril(x).T J).T J).T
     """
-    if lower or not right:
-        raise _capi.NpwError("trsm: only lower=False, right=True (the LambdaPACK call form) is implemented on B200")
-    return trsm_with_inverse(x, y, None)
+    _check_tile(x, "x")
+    _check_tile(y, "y")
+    if right and not lower:
+        return trsm_with_inverse(x, y, None)
+    if right and lower:
+        # A = tril(x.T) = triu(x).T : solve X A = y  ->  X = y inv(U).T, U = triu(x); L' = J U J is lower triangular
+        Lp = torch.flip(x, (0, 1)).contiguous()
+        return torch.flip(trsm_with_inverse(Lp, torch.flip(y, (1,)).contiguous(), None), (1,)).contiguous()
+    if lower:
+        # left, A = tril(x.T) = triu(x).T =: L'' (lower): X = inv(L'') y  ->  X.T = y.T inv(L'').T  with L'' = triu(x).T
+        return transpose(trsm_with_inverse(transpose(x), transpose(y), None))
+    # left, A = triu(x.T) = tril(x).T =: U' (upper): X = inv(U') y  ->  X.T = y.T inv(U').T ; J U' J is lower triangular
+    Lp = torch.flip(transpose(x), (0, 1)).contiguous()
+    Xt = torch.flip(trsm_with_inverse(Lp, torch.flip(transpose(y), (1,)).contiguous(), None), (1,))
+    return transpose(Xt.contiguous())
 
 
 def _trsm_flops(x, y):

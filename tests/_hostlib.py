@@ -38,6 +38,17 @@ class HostLib:
     def npw_tpqrt_work_bytes(self, n):
         return 8
 
+    def npw_trsm_work_bytes(self, m, n):
+        return 8
+
+    def npw_trsm_rlt_f64(self, B_out, ldbo, L, ldl, B, ldb, m, n, invdiag, work, stream):
+        """include/npw_b200.h: B_out = B inv(tril(L)).T (the strict upper triangle of L is ignored)."""
+        self.calls.append(("trsm_rlt", m, n))
+        l = np.tril(np.array(_view(L, n, n, ldl)))
+        b = np.array(_view(B, m, n, ldb))
+        _view(B_out, m, n, ldbo)[...] = scipy.linalg.solve_triangular(l, b.T, lower=True).T
+        return 0
+
     # -- kernels (semantics: include/npw_b200.h)
     def npw_gemm_f64(self, C, ldc, C0, ldc0, A, lda, transA, B, ldb, transB, m, n, k, alpha, beta, stream):
         self.calls.append(("gemm", m, n, k, transA, transB))

@@ -150,12 +150,19 @@ def test_chol_not_positive_definite_raises_linalgerror(cuda_device):
         kernels.chol(torch.zeros(4, 5, dtype=torch.float64, device=cuda_device))
 
 
-def test_trsm_only_supports_the_dsl_call_form(cuda_device):
-    t = torch.eye(4, dtype=torch.float64, device=cuda_device)
-    with pytest.raises(_capi.NpwError):
-        kernels.trsm(t, t, lower=True)
-    with pytest.raises(_capi.NpwError):
-        kernels.trsm(t, t, right=False)
+@pytest.mark.parametrize("lower", [False, True])
+@pytest.mark.parametrize("right", [True, False])
+def test_trsm_all_flag_combinations_match_blas(cuda_device, lower, right):
+    """kernels.trsm(x, y, lower, right) = dtrsm(1.0, x.T, y, lower, side=right) (kernels.py:254-257); the three forms the
+    DSL never uses are mapped onto the one native solve by transposes and index reversal."""
+    import scipy.linalg
+    rs = np.random.RandomState(int(lower) * 2 + int(right))
+    n, m = 200, 136
+    x = rs.randn(n, n) / n + np.eye(n)                      # well conditioned; FULL matrix: only one triangle may be read
+    y = rs.randn(m, n) if right else rs.randn(n, m)
+    want = np.ascontiguousarray(scipy.linalg.blas.dtrsm(1.0, x.T, y, lower=int(lower), side=int(right)))
+    got = kernels.trsm(dev(x, cuda_device), dev(y, cuda_device), lower=lower, right=right)
+    assert rel(got, want) < TOL
 
 
 def test_trsm_ill_conditioned_factor_still_within_tolerance(cuda_device):

@@ -201,3 +201,19 @@ def test_gemm_kloop_program_matches_the_legacy_binops_schedule(host, unique_key)
     close(C, a @ b, 1e-12)
     # large tiles go to the DMMA core in NT form after the transpose kernel re-lays B out; accumulation aliases C0 = C
     assert any(c[0] == "copy2d" and c[3] == 1 for c in host.calls)
+
+
+@pytest.mark.parametrize("lower", [False, True])
+@pytest.mark.parametrize("right", [True, False])
+def test_trsm_flag_combinations_map_onto_the_one_native_solve(host, lower, right):
+    """kernels.trsm(x, y, lower, right) = scipy.linalg.blas.dtrsm(1.0, x.T, y, lower=lower, side=int(right))
+    (kernels.py:254-257) for all four flag combinations, with a FULL (non-triangular) x: BLAS reads one triangle only."""
+    import scipy.linalg
+    rs = np.random.RandomState(int(lower) * 2 + int(right))
+    n, m = 24, 40
+    x = rs.randn(n, n) + 6 * np.eye(n)
+    y = rs.randn(m, n) if right else rs.randn(n, m)
+    want = scipy.linalg.blas.dtrsm(1.0, x.T, y, lower=int(lower), side=int(right))
+    got = kernels.trsm(T(x), T(y), lower=lower, right=right)
+    close(got, np.ascontiguousarray(want), 1e-12)
+    assert [c for c in host.calls if c[0] == "trsm_rlt"]            # all of them end in npw_trsm_rlt_f64
