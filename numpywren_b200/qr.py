@@ -87,15 +87,27 @@ def qr_factor(*blocks, **kwargs):
         if b.shape[1] != n:
             raise ValueError("all the input array dimensions except for the concatenation axis must match exactly")
     m = sum(b.shape[0] for b in blocks)
-    if n > m:
-        raise _capi.NpwError("qr_factor: wide inputs (n > m) take the reference's slow_qr path, which is off the hot path")
-    V = torch.empty((m, n), dtype=torch.float64, device=blocks[0].device)
+    dev = blocks[0].device
+    A = torch.empty((m, n), dtype=torch.float64, device=dev)
     # np.vstack: the stacked copy becomes the working matrix that V overwrites
     r0 = 0
     for b in blocks:
-        _copy_into(V[r0:r0 + b.shape[0]], b)
+        _copy_into(A[r0:r0 + b.shape[0]], b)
         r0 += b.shape[0]
-    return _geqrt_inplace(V)
+    if n <= m:
+        return _geqrt_inplace(A)
+    # wide input (reference fast_qr -> slow_qr, kernels.py:67-84,94-95: dgeqrf + dlarft): the m reflectors come from the
+    # leading m x m block alone; the remaining columns only receive Q^T:  R = [R1 | A2 - V T^T (V^T A2)]
+    V = torch.empty((m, m), dtype=torch.float64, device=dev)
+    _copy_into(V, A[:, :m])
+    V, T, R1 = _geqrt_inplace(V)
+    A2 = A[:, m:]
+    W = _gemm_any(_new(m, n - m, A), None, V, A2, True, False, 1.0, 0.0)
+    W2 = _gemm_any(_new(m, n - m, A), None, T, W, True, False, 1.0, 0.0)
+    R = torch.empty((m, n), dtype=torch.float64, device=dev)
+    _copy_into(R[:, :m], R1)
+    _gemm_any(R[:, m:], A2, V, W2, False, False, -1.0, 1.0)
+    return V, T, R
 
 
 def qr_factor_triangular(x0, x1, **kwargs):

@@ -81,6 +81,31 @@ def identity(x):
     return x
 
 
+def _larft_forward_columnwise(v, tau):
+    """LAPACK dlarft(direct='F', storev='C'): the upper-triangular T of the block reflector I - V T V^T."""
+    k = v.shape[1]
+    t = np.zeros((k, k))
+    for i in range(k):
+        t[i, i] = tau[i]
+        if i > 0:
+            t[:i, i] = -tau[i] * (t[:i, :i] @ (v[:, :i].T @ v[:, i]))
+    return t
+
+
+def slow_qr(x):
+    """kernels.py:67-84 (dgeqrf + the f2py dlarft module, restated above): the path fast_qr takes for wide inputs
+    (n > m).  Returns v (m x k, unit lower), t (k x k), r (k x n upper trapezoidal), k = min(m, n)."""
+    qr, tau, work, info = scipy.linalg.lapack.dgeqrf(a=x)
+    if info != 0:
+        raise RuntimeError(f"dgeqrf info={info}")
+    r = np.triu(qr)
+    k = min(x.shape[0], x.shape[1])
+    v = np.tril(qr)[:, :k].copy()
+    v[np.diag_indices(k)] = 1
+    r = r[:r.shape[1], :]
+    return v, _larft_forward_columnwise(v, tau), r
+
+
 def fast_qr(x):
     """kernels.py:86-105 with scipy's dgeqrt standing in for the f2py dgeqrt3 module.
 
@@ -90,7 +115,7 @@ def fast_qr(x):
     m, n = x.shape
     k = min(m, n)
     if n > m:
-        raise NotImplementedError("slow_qr path (kernels.py:67-84) is off the hot path")
+        return slow_qr(x)                                     # kernels.py:94-95
     a, t, info = scipy.linalg.lapack.dgeqrt(n, np.asfortranarray(x))
     if info != 0:
         raise RuntimeError(f"dgeqrt info={info}")

@@ -213,3 +213,16 @@ def test_bdfac_householder_semantics_meet_the_reference_test(n, b):
     m = orc.run_bdfac(A, semantics="householder")
     fac = orc.bdfac_assemble(m["R_QR"], m["L_LQ"], n, b)
     np.testing.assert_allclose(np.linalg.svd(fac, compute_uv=False), np.linalg.svd(X, compute_uv=False), rtol=1e-10, atol=1e-12)
+
+
+def test_slow_qr_restatement_agrees_with_geqrt_on_the_leading_block():
+    """kernels.py:67-84: for a wide matrix the reflectors (and dlarft's T) depend on the leading m x m block only."""
+    a = np.random.RandomState(8).randn(20, 50)
+    v, t, r = orc.slow_qr(a)
+    v1, t1, r1 = orc.fast_qr(np.ascontiguousarray(a[:, :20]))
+    np.testing.assert_allclose(v, v1, atol=1e-13)
+    np.testing.assert_allclose(t, t1, atol=1e-13)
+    np.testing.assert_allclose(r[:, :20], r1, atol=1e-13)
+    q = np.eye(20) - v @ t @ v.T
+    np.testing.assert_allclose(q @ r, a, atol=1e-12)
+    assert r.shape == (20, 50) and not np.tril(r, -1).any()

@@ -277,3 +277,12 @@ def test_gemm_kloop_program(unique_key, cuda_device, shape, tile):
     assert np.array_equal(A.numpy(), a) and np.array_equal(B.numpy(), b)
     for mm in meta["outputs"] + meta["intermediates"] + [A, B]:
         mm.free()
+
+
+@pytest.mark.parametrize("m,n", [(12, 30), (130, 400)])
+def test_qr_factor_wide_input_takes_the_slow_qr_path(cuda_device, m, n):
+    """n > m: reference fast_qr -> slow_qr (dgeqrf + dlarft, kernels.py:67-84,94-95)."""
+    a = np.random.RandomState(m).randn(m, n)
+    v, t, r = kernels.qr_factor(torch.from_numpy(a).to(cuda_device))
+    vo, to, ro = orc.qr_factor(a)
+    close(v, vo); close(t, to); close(r, ro)

@@ -217,3 +217,16 @@ def test_trsm_flag_combinations_map_onto_the_one_native_solve(host, lower, right
     got = kernels.trsm(T(x), T(y), lower=lower, right=right)
     close(got, np.ascontiguousarray(want), 1e-12)
     assert [c for c in host.calls if c[0] == "trsm_rlt"]            # all of them end in npw_trsm_rlt_f64
+
+
+@pytest.mark.parametrize("m,n", [(12, 30), (130, 400)])
+def test_qr_factor_wide_input_takes_the_slow_qr_path(host, m, n):
+    """n > m: reference fast_qr falls back to slow_qr (dgeqrf + dlarft, kernels.py:67-84,94-95): v m x m, t m x m,
+    r m x n upper trapezoidal."""
+    a = np.random.RandomState(m).randn(m, n)
+    v, t, r = kernels.qr_factor(T(a))
+    vo, to, ro = orc.qr_factor(a)
+    assert tuple(v.shape) == (m, m) and tuple(t.shape) == (m, m) and tuple(r.shape) == (m, n)
+    close(v, vo, 1e-12); close(t, to, 1e-12); close(r, ro, 1e-12)
+    q = np.eye(m) - vo @ to @ vo.T
+    close(q @ ro, a, 1e-12)
