@@ -15,7 +15,14 @@ timeout 600 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.json 2> gpur
 for s in 5 6 8; do timeout 300 python tools/ozaki_lib_probe.py --size 4096 --digits $s 2>&1 | tail -1 | tee -a gpurun_out/ozaki_lib_probe.jsonl; done
 # 4a. tcgen05 building blocks in isolation (hand-swizzled shared memory, one MMA group, tcgen05.ld): tells descriptor
 #     errors apart from TMA / barrier errors before the product kernel is tried
-nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o /tmp/tcgen05_i8_probe tools/tcgen05_i8_probe.cu && timeout 60 /tmp/tcgen05_i8_probe 2>&1 | tail -12 | tee gpurun_out/tcgen05_i8_probe.log
+nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o /tmp/tcgen05_i8_probe tools/tcgen05_i8_probe.cu
+timeout 30 /tmp/tcgen05_i8_probe 2>&1 | tail -12 | tee gpurun_out/tcgen05_i8_probe.log
+if ! grep -q "PROBE OK" gpurun_out/tcgen05_i8_probe.log; then
+  # alternative descriptor encodings (lbo sbo layout version), one process each
+  for v in "0 64 2 1" "64 64 2 1" "1 64 2 0" "1 8 2 1" "1 64 1 1"; do
+    timeout 30 /tmp/tcgen05_i8_probe $v 2>&1 | tail -4 | tee -a gpurun_out/tcgen05_i8_probe.log
+  done
+fi
 # 4b. the never-run tcgen05 int8 kernel, smallest case first, each under its own timeout (a hang must not cost the box)
 for t in "test_split_i8_matches_the_prototype_bit_for_bit" "test_syrk_i8emu_matches_the_prototype[128-64-128-1]" \
          "test_syrk_i8emu_matches_the_prototype[128-64-128-6]" "test_syrk_i8emu_matches_the_prototype" \

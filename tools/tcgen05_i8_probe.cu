@@ -7,6 +7,9 @@
 //   3. tcgen05.commit -> mbarrier, four warps tcgen05.ld the 128 x 64 int32 accumulator and compare with a host product.
 // Build + run (B200 only):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O2 -o tools/tcgen05_i8_probe tools/tcgen05_i8_probe.cu && timeout 60 tools/tcgen05_i8_probe
+// Descriptor fields can be overridden from the command line to try alternative encodings in separate processes (a bad
+// encoding may poison the context):   tcgen05_i8_probe [lbo=1] [sbo=64] [layout=2] [version=1]
+// (defaults = what csrc/npw_ozaki_i8.cu uses; tools/round2_first_call.sh sweeps a few, each under its own timeout).
 // Prints "PROBE OK" or the first mismatches (which tell descriptor / lane-mapping errors apart: a transposed or
 // row-permuted result points at the descriptors, a quadrant shift at the tcgen05.ld lane field).
 #include <cuda_runtime.h>
@@ -18,17 +21,21 @@ constexpr int M = 128, N = 64, KB = 128, UK = 32;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr) {
+struct DescCfg {
+  uint32_t lbo, sbo, layout, version;
+};
+
+__device__ __forceinline__ uint64_t umma_desc_k128(uint32_t smem_addr, DescCfg c) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
-  d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
-  d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(c.lbo & 0x3FFFu) << 16;
+  d |= static_cast<uint64_t>(c.sbo & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(c.version & 3u) << 46;
+  d |= static_cast<uint64_t>(c.layout & 7u) << 61;
   return d;
 }
 
-__global__ void __launch_bounds__(192) probe(const int8_t* A, const int8_t* B, int32_t* D) {
+__global__ void __launch_bounds__(192) probe(const int8_t* A, const int8_t* B, int32_t* D, DescCfg cfg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sa = smem;                 // 128 rows x 128 B
   uint8_t* sb = smem + M * KB;        // 64 rows x 128 B
@@ -60,7 +67,7 @@ __global__ void __launch_bounds__(192) probe(const int8_t* A, const int8_t* B, i
   if (warp == 1 && lane == 0) {
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
     for (int k4 = 0; k4 < KB / UK; ++k4) {
-      const uint64_t ad = umma_desc_k128(smem_u32(sa) + k4 * UK), bd = umma_desc_k128(smem_u32(sb) + k4 * UK);
+      const uint64_t ad = umma_desc_k128(smem_u32(sa) + k4 * UK, cfg), bd = umma_desc_k128(smem_u32(sb) + k4 * UK, cfg);
       const uint32_t acc = k4 > 0 ? 1u : 0u;
       asm volatile(
           "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -98,7 +105,13 @@ __global__ void __launch_bounds__(192) probe(const int8_t* A, const int8_t* B, i
   }
 }
 
-int main() {
+int main(int argc, char** argv) {
+  DescCfg cfg = {1u, 64u, 2u, 1u};
+  if (argc > 1) cfg.lbo = static_cast<uint32_t>(atoi(argv[1]));
+  if (argc > 2) cfg.sbo = static_cast<uint32_t>(atoi(argv[2]));
+  if (argc > 3) cfg.layout = static_cast<uint32_t>(atoi(argv[3]));
+  if (argc > 4) cfg.version = static_cast<uint32_t>(atoi(argv[4]));
+  printf("descriptor: lbo=%u sbo=%u layout=%u version=%u\n", cfg.lbo, cfg.sbo, cfg.layout, cfg.version);
   int8_t *hA = (int8_t*)malloc(M * KB), *hB = (int8_t*)malloc(N * KB);
   int32_t* hD = (int32_t*)malloc(M * N * 4);
   srand(1);
@@ -112,7 +125,7 @@ int main() {
   cudaMemset(dD, 0xff, M * N * 4);
   const int smem = M * KB + N * KB + 64;
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  probe<<<1, 192, smem>>>(dA, dB, dD);
+  probe<<<1, 192, smem>>>(dA, dB, dD, cfg);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("PROBE CUDA ERROR: %s\n", cudaGetErrorString(e)); return 2; }
   cudaMemcpy(hD, dD, M * N * 4, cudaMemcpyDeviceToHost);
