@@ -447,6 +447,7 @@ def _engine_for(program: lp.LambdaPackProgram, **opts) -> TileEngine:
         prio = eng.priorities()
         compiled = program.program
         program._priority_fn = lambda e, v: prio[compiled.node(e, v).nid]
+        program._prio_by_nid = prio
     return eng
 
 
@@ -501,28 +502,30 @@ def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, 
     eng = _engine_for(program, **_engine_options(pipeline_width, streams, high_streams, inplace, consume_inputs, profile,
                                                  free_intermediates))
     program._defer_success = True
+    nodes = program.program.nodes
     executed, refs = [], []
     try:
         while program.program_status() == lp.PS.RUNNING:
             if time.time() - lambda_start > timeout:
                 break
-            item = program._dequeue()
+            item = program._dequeue_item()
             if item is None:
                 break
-            expr_idx, var_values = item
-            status = program.get_node_status(expr_idx, var_values)
+            expr_idx, frozen, nid = item
+            node = nodes[nid] if nid is not None else program.program.node(expr_idx, dict(frozen))
+            var_values = node.var_values
+            status = program.node_status_of(node)
             if status == lp.NS.FINISHED:
                 program.incr_repeated_finish()
                 continue
             if status == lp.NS.NOT_READY:
                 program.incr_not_ready()
                 continue
-            node = program.program.node(expr_idx, var_values)
             try:
                 if status in (lp.NS.READY, lp.NS.RUNNING):
                     if status == lp.NS.RUNNING:
                         program.incr_repeated_compute()
-                    program.set_node_status(expr_idx, var_values, lp.NS.RUNNING)
+                    program.set_node_status_of(node, lp.NS.RUNNING)
                     comm = eng.comm
                     if comm is not None:
                         comm.before_node(node, eng)
@@ -532,8 +535,8 @@ def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, 
                         comm.after_node(node, eng)
                 else:
                     program.incr_repeated_post_op()
-                program.post_op(expr_idx, var_values, lp.PS.SUCCESS, None)
-                program.set_node_status(expr_idx, var_values, lp.NS.FINISHED)
+                program.post_op_node(node, lp.PS.SUCCESS)
+                program.set_node_status_of(node, lp.NS.FINISHED)
             except Exception:
                 tb = traceback.format_exc()
                 program.handle_exception("EXCEPTION", tb=tb, expr_idx=expr_idx, var_values=var_values)

@@ -301,6 +301,24 @@ class LambdaPackProgram(object):
         return "{0}_{1}_{2}".format(self.hash, self._node_str(expr_idx1, var_values1),
                                     self._node_str(expr_idx2, var_values2))
 
+    def _node_str_of(self, node):
+        """_node_str of an expanded node, formatted once (the reference re-formats these Redis keys on every access;
+        with ~15 accesses per node that was half of the host loop's time)."""
+        cache = self.__dict__.setdefault("_nstr_cache", {})
+        s = cache.get(node.nid)
+        if s is None:
+            s = cache[node.nid] = self._node_str(node.expr_idx, node.var_values)
+        return s
+
+    def node_status_of(self, node):
+        with self._lock:
+            return self._node_status.get(self._node_str_of(node), NS.NOT_READY)
+
+    def set_node_status_of(self, node, status):
+        with self._lock:
+            self._node_status[self._node_str_of(node)] = status
+        return status
+
     # ------------------------------------------------------------------ node / program status
     def get_node_status(self, expr_idx, var_values):
         with self._lock:
@@ -341,14 +359,28 @@ class LambdaPackProgram(object):
             priority = fn(expr_idx, var_values) if fn is not None else 0
         with self._lock:
             self._seq += 1
-            heapq.heappush(self._ready, (-priority, self._seq, int(expr_idx), tuple(sorted(var_values.items()))))
+            heapq.heappush(self._ready, (-priority, self._seq, int(expr_idx), tuple(sorted(var_values.items())), None))
+
+    def _enqueue_node(self, node, priority):
+        """Same queue, for a node of the expanded DAG (no key formatting: the host loop's fast path)."""
+        with self._lock:
+            self._seq += 1
+            heapq.heappush(self._ready, (-priority, self._seq, node.expr_idx, node.key[1], node.nid))
 
     def _dequeue(self):
         with self._lock:
             if not self._ready:
                 return None
-            _, _, e, v = heapq.heappop(self._ready)
+            _, _, e, v, _ = heapq.heappop(self._ready)
             return e, dict(v)
+
+    def _dequeue_item(self):
+        """-> (expr_idx, frozen var_values, node id or None) of the highest-priority ready node, or None."""
+        with self._lock:
+            if not self._ready:
+                return None
+            _, _, e, v, nid = heapq.heappop(self._ready)
+            return e, v, nid
 
     def queue_depth(self):
         with self._lock:
@@ -413,6 +445,52 @@ class LambdaPackProgram(object):
         except Exception as e:
             tb = traceback.format_exc()
             self.handle_exception("POST OP EXCEPTION", tb=tb, expr_idx=expr_idx, var_values=var_values)
+            raise
+
+    def post_op_node(self, node, ret_code):
+        """``post_op`` for a node of the expanded DAG: identical state transitions and keys (edge sums, READY marks,
+        terminator set — the public accessors see the same dictionaries), but children / parents come straight from the
+        DAG arrays and every key string is formatted once per node instead of once per access."""
+        try:
+            nodes = self.program.nodes
+            me = self._node_str_of(node)
+            prio = getattr(self, "_prio_by_nid", None)
+            ready_children = []
+            with self._lock:
+                self._node_status[me] = NS.POST_OP
+                for c in node.children:
+                    child = nodes[c]
+                    cs = self._node_str_of(child)
+                    edge = "{0}_{1}_{2}".format(self.hash, me, cs)
+                    ckey = "{0}_{1}_edgesum".format(self.hash, cs)
+                    if edge not in self._edges_seen:
+                        self._edges_seen.add(edge)
+                        self._edge_sum[ckey] = self._edge_sum.get(ckey, 0) + 1
+                    if self._edge_sum.get(ckey, 0) == len(child.parents) and \
+                            self._node_status.get(cs, NS.NOT_READY) != NS.FINISHED:
+                        self._node_status[cs] = NS.READY
+                        ready_children.append(child)
+            next_operator = None
+            if self.eager and ready_children:
+                last = ready_children.pop()
+                next_operator = last.ref
+            for child in ready_children:
+                if prio is not None:
+                    self._enqueue_node(child, prio[child.nid])
+                else:
+                    self._enqueue(child.expr_idx, child.var_values)
+            self.incr_progress()
+            if self.program.is_terminator(node.expr_idx):
+                with self._lock:
+                    self._terminators_done.add(me)
+                    if len(self._terminators_done) == self.program.num_terminators:
+                        self._all_terminators_done = True
+                        if not getattr(self, "_defer_success", False):
+                            self.return_success()
+            return next_operator, None
+        except Exception as e:
+            tb = traceback.format_exc()
+            self.handle_exception("POST OP EXCEPTION", tb=tb, expr_idx=node.expr_idx, var_values=node.var_values)
             raise
 
     # ------------------------------------------------------------------ counters (reference :683-752)

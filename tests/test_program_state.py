@@ -128,3 +128,52 @@ def test_lru_cache_and_busy_time():
     with pytest.raises(KeyError):
         c["b"]
     assert job_runner.calculate_busy_time([[0, 2], [1, 3], [5, 6]]) == [[0, 3], [5, 6]]
+
+
+def test_fast_host_loop_keeps_the_reference_bookkeeping(unique_key, monkeypatch):
+    """job_runner's loop uses post_op_node / node-id queue items (keys formatted once per node); the resulting state —
+    node status, edge sums, counted edges, terminators, order of execution — must be exactly what the public
+    post_op path (the reference's protocol, key for key) produces."""
+    from numpywren_b200.alg_wrappers import cholesky
+
+    def strip(d, h):
+        return {k.replace(h, "H"): v for k, v in d.items()} if isinstance(d, dict) else {k.replace(h, "H") for k in d}
+
+    # A: the engine loop with a recording engine (fast path)
+    A1 = BigMatrix(unique_key("fa"), shape=(24, 24), shard_sizes=(4, 4), device="cpu")
+    prog_a, _ = cholesky(A1)
+    order_a = []
+    monkeypatch.setattr(job_runner.TileEngine, "run_node", lambda self, node: order_a.append(node.key))
+    monkeypatch.setattr(job_runner.TileEngine, "finish", lambda self: [])
+    job_runner.prepare(prog_a)
+    prog_a.start()
+    out = job_runner.lambdapack_run(prog_a, timeout=60)
+    assert prog_a.program_status() == lp.PS.SUCCESS and len(out["executed_messages"]) == len(prog_a.program.nodes)
+    # B: the public pieces (dequeue -> post_op -> set_node_status), same priorities
+    A2 = BigMatrix(unique_key("fb"), shape=(24, 24), shard_sizes=(4, 4), device="cpu")
+    prog_b, _ = cholesky(A2)
+    prio = job_runner.TileEngine(prog_b).priorities()
+    compiled = prog_b.program
+    prog_b._priority_fn = lambda e, v: prio[compiled.node(e, v).nid]
+    prog_b.start()
+    order_b = []
+    while True:
+        item = prog_b._dequeue()
+        if item is None:
+            break
+        e, v = item
+        assert prog_b.get_node_status(e, v) == lp.NS.READY
+        prog_b.set_node_status(e, v, lp.NS.RUNNING)
+        prog_b.post_op(e, v, lp.PS.SUCCESS, None)
+        prog_b.set_node_status(e, v, lp.NS.FINISHED)
+        order_b.append(compiled.node(e, v).key)
+    assert order_a == order_b
+    ha, hb = prog_a.hash, prog_b.hash
+    assert strip(prog_a._node_status, ha) == strip(prog_b._node_status, hb)
+    assert strip(prog_a._edge_sum, ha) == strip(prog_b._edge_sum, hb)
+    assert strip(prog_a._edges_seen, ha) == strip(prog_b._edges_seen, hb)
+    assert prog_a._terminators_done == prog_b._terminators_done
+    assert prog_a._get("progress") == prog_b._get("progress") == len(compiled.nodes)
+    # public accessors see the fast path's state
+    n0 = prog_a.program.nodes[0]
+    assert prog_a.get_node_status(n0.expr_idx, n0.var_values) == lp.NS.FINISHED
