@@ -37,6 +37,15 @@ UNIT = "TFLOP/s"
 
 
 # ----------------------------------------------------------------------------------------------- helpers
+def _dtype_label():
+    """Arithmetic the path computes in.  "f64" unless the EXPERIMENTAL int8-tensor-core emulation of the syrk products was
+    switched on explicitly (NPW_B200_SYRK=i8emu) — then the line says so instead of claiming plain fp64."""
+    if os.environ.get("NPW_B200_SYRK", "native") == "i8emu":
+        return "f64 (syrk products emulated on int8 tensor cores, %s digits; trsm/potrf native f64)" % os.environ.get(
+            "NPW_B200_I8_DIGITS", "6")
+    return "f64"
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -405,7 +414,7 @@ def run_gpu_arm(args):
                "sample": f"oracle run_cholesky N={args.cpu_n} tile={b} ({t_cpu:.1f} s on the host cores)"}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": _dtype_label(),
             "data": "synthetic",
             "config": {"workload": workload_name(args), "tile_tasks": wl.nb * (wl.nb + 1) * (wl.nb + 2) // 6,
                        "l2": "inputs larger than L2 (18+ GiB of tiles per step; every step regenerates its input)",

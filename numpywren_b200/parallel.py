@@ -583,8 +583,9 @@ def bench_main(args, metric, unit, workload):
             e2e["error"] = "another rank could not stage its host buffers"
         del host_in, host_out
     if grid.rank == 0:
+        from bench import _dtype_label
         line = {"metric": metric, "value": value, "unit": unit, "n_gpus": grid.world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": _dtype_label(),
                 "data": "synthetic",
                 "config": {"workload": workload, "process_grid": f"{grid.P}x{grid.Q} block-cyclic over tile index",
                            "exchange": os.environ.get("NPW_B200_EXCHANGE", "symm"),
