@@ -366,7 +366,7 @@ class TileEngine:
         n = self._digit_uses.get(key)
         if n is None:
             n = 0
-            for nid in self.compiled._readers.get(key, ()):
+            for nid in set(self.compiled._readers.get(key, ())):   # a diagonal update lists the tile twice
                 nd = self.compiled.nodes[nid]
                 if nd.call.compute is kernels.syrk and len(nd.reads) == 3:
                     n += sum(1 for j in (1, 2) if _tile_key(*nd.reads[j]) == key)

@@ -177,3 +177,40 @@ def test_fast_host_loop_keeps_the_reference_bookkeeping(unique_key, monkeypatch)
     # public accessors see the fast path's state
     n0 = prog_a.program.nodes[0]
     assert prog_a.get_node_status(n0.expr_idx, n0.var_values) == lp.NS.FINISHED
+
+
+def test_i8emu_digit_cache_is_released_after_the_last_syrk(unique_key, monkeypatch):
+    """The experimental int8 path caches a panel tile's digits for the syrks that read it (like invdiag); the reference
+    count must reach zero exactly when the last of them has been enqueued — no leak, no early drop."""
+    import torch
+    from numpywren_b200 import kernels
+    from numpywren_b200.alg_wrappers import cholesky
+    from numpywren_b200.compiler import _tile_key
+
+    class Ev:
+        def record(self, stream): pass
+
+    splits = []
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(kernels, "split_i8", lambda tile, digits: (splits.append(tile) or ("d%d" % len(splits), "e")))
+    A = BigMatrix(unique_key("dc"), shape=(28, 28), shard_sizes=(4, 4), device="cpu")
+    program, _ = cholesky(A)
+    eng = job_runner.TileEngine(program)
+    live_max = 0
+    stream = object()
+    for node in program.program.nodes:                       # program order is a valid enqueue order
+        if node.call.compute_name != "syrk":
+            continue
+        keys = [_tile_key(m, idx) for m, idx in node.reads]
+        d1 = eng._tile_digits(node, 1, ("tile", keys[1]), keys[1], stream)
+        d2 = eng._tile_digits(node, 2, ("tile", keys[2]), keys[2], stream)
+        assert d1 is not None and d2 is not None
+        if keys[1] == keys[2]:
+            assert d1 == d2                                   # diagonal update: one extraction serves both operands
+        live_max = max(live_max, len(eng._digits))
+        eng._release_digits(keys[1])
+        eng._release_digits(keys[2])
+    nb = 7
+    assert len(eng._digits) == 0                              # everything released
+    assert len(splits) == nb * (nb - 1) // 2                  # each panel tile O[j,i] (j > i) is split exactly once
+    assert live_max <= nb * (nb - 1) // 2
