@@ -214,3 +214,51 @@ def test_i8emu_digit_cache_is_released_after_the_last_syrk(unique_key, monkeypat
     assert len(eng._digits) == 0                              # everything released
     assert len(splits) == nb * (nb - 1) // 2                  # each panel tile O[j,i] (j > i) is split exactly once
     assert live_max <= nb * (nb - 1) // 2
+
+
+@pytest.mark.parametrize("which", ["qr", "bdfac", "gemm", "gemm_kloop"])
+def test_dead_tile_reclamation_never_drops_a_tile_that_is_still_needed(unique_key, which):
+    """free_intermediates: walking the DAG in a valid order with the engine's own release logic, every written tile must
+    still be in the store when a reader comes for it, inputs / outputs are never touched, and every intermediate that
+    was read at all is gone at the end."""
+    import torch
+    from numpywren_b200 import alg_wrappers
+    from numpywren_b200.compiler import _tile_key
+
+    A = BigMatrix(unique_key("ra"), shape=(24, 24), shard_sizes=(4, 4), device="cpu")
+    B = BigMatrix(unique_key("rb"), shape=(24, 24), shard_sizes=(4, 4), device="cpu")
+    for m in (A, B):
+        for bi in m.block_idxs:
+            m._put_block_ref(torch.zeros(4, 4, dtype=torch.float64), *bi)
+    program, meta = (getattr(alg_wrappers, which)(A, B) if which.startswith("gemm") else getattr(alg_wrappers, which)(A))
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    cp = program.program
+    eng = job_runner.TileEngine(program, free_intermediates=True)
+    assert eng.free_intermediates
+    keep = {id(m) for m in [A, B] + meta["outputs"]}
+    starters = {(int(e), tuple(sorted((str(k), int(v)) for k, v in vv.items()))) for e, vv in cp.starters}
+    ran = set()
+    for node in cp.nodes:
+        if node.key not in starters and not (node.parents and all(p in ran for p in node.parents)):
+            continue
+        refs, keys = [], []
+        for (m, idx) in node.reads:
+            ref = m._get_block_ref(*idx)
+            if cp.writer_of(m, idx) is not None:
+                assert ref is not None, f"{which}: tile {m.key}{list(idx)} was dropped before {node} read it"
+            refs.append(ref)
+            keys.append(_tile_key(m, idx))
+        for (m, idx) in node.writes:
+            m._put_block_ref(torch.zeros(1, 1, dtype=torch.float64), *idx)
+        eng._release_dead_inputs(node, refs, keys, None)
+        ran.add(node.nid)
+    assert eng.freed_tiles > 0
+    for m in [A, B] + meta["outputs"]:
+        assert len(m._blocks_store) > 0                                        # never touched
+    for m in meta["intermediates"]:
+        if id(m) in keep:
+            continue
+        for idx in list(m._blocks_store):
+            assert cp.num_readers(m, idx) == 0 or any(cp.nodes[r].nid not in ran for r in cp._readers[_tile_key(m, idx)]), \
+                f"{which}: {m.key}{list(idx)} was read by every consumer but not reclaimed"
