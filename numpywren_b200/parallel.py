@@ -243,8 +243,9 @@ class TileExchange:
         if ent is None:
             return None
         buf, work = ent
-        with torch.cuda.stream(stream):
-            work.wait()                 # stream-level wait on the NCCL receive, the host does not block
+        if not work.is_completed():     # a finished receive needs no ordering (and gloo must not be waited on twice)
+            with torch.cuda.stream(stream):
+                work.wait()             # stream-level wait on the NCCL receive, the host does not block
         buf.record_stream(stream)
         return buf
 

@@ -46,7 +46,7 @@ class HostLib:
         self.calls.append(("trsm_rlt", m, n))
         l = np.tril(np.array(_view(L, n, n, ldl)))
         b = np.array(_view(B, m, n, ldb))
-        _view(B_out, m, n, ldbo)[...] = scipy.linalg.solve_triangular(l, b.T, lower=True).T
+        _view(B_out, m, n, ldbo)[...] = scipy.linalg.solve_triangular(l, b.T, lower=True, check_finite=False).T
         return 0
 
     # -- kernels (semantics: include/npw_b200.h)
@@ -108,6 +108,52 @@ class HostLib:
         _view(R, n, n, ldr)[...] = np.triu(qr)[:n]
         return 0
 
+
+    # -- Cholesky-path entry points (so that the whole stream engine can be exercised on the host, tests/_fakecuda.py)
+    def npw_syrk_f64(self, C, ldc, S, lds, X, ldx, Y, ldy, m, n, k, stream):
+        self.calls.append(("syrk", m, n, k))
+        _view(C, m, n, ldc)[...] = np.array(_view(S, m, n, lds)) - _view(X, m, k, ldx) @ _view(Y, n, k, ldy).T
+        return 0
+
+    def npw_syrk_lower_f64(self, C, ldc, S, lds, X, ldx, Y, ldy, m, n, k, stream):
+        """Only the 128 x 128 tiles touching the lower triangle are updated; the others keep S (out of place) / are left
+        alone (in place) — include/npw_b200.h."""
+        self.calls.append(("syrk_lower", m, n, k))
+        full = np.array(_view(S, m, n, lds)) - _view(X, m, k, ldx) @ _view(Y, n, k, ldy).T
+        i, j = np.indices((m, n))
+        low = (j // 128) * 128 <= (i // 128) * 128 + 127
+        out = np.array(_view(S, m, n, lds))
+        out[low] = full[low]
+        _view(C, m, n, ldc)[...] = out
+        return 0
+
+    def npw_invdiag_bytes(self, n):
+        return 8 * max(1, ((n + 127) // 128) * 128 * 128)
+
+    def npw_potrf_work_bytes(self, n):
+        return 8
+
+    def npw_trtri_diag_f64(self, invdiag, L, ldl, n, stream):
+        self.calls.append(("trtri_diag", n))
+        return 0
+
+    def npw_potrf_l_f64(self, L_out, ldl, A, lda, n, info, invdiag, work, stream):
+        self.calls.append(("potrf", n))
+        a = np.tril(np.array(_view(A, n, n, lda)))
+        a = a + np.tril(a, -1).T
+        code = 0
+        try:
+            l = np.linalg.cholesky(a)
+        except np.linalg.LinAlgError:
+            l, code = np.eye(n), 1          # the CUDA kernel leaves NaNs; any finite stand-in keeps later host calls alive
+        _view(L_out, n, n, ldl)[...] = l
+        ctypes.cast(ctypes.c_void_p(int(info)), ctypes.POINTER(ctypes.c_int32))[0] = code
+        return 0
+
+    def npw_mul_f64(self, out, x, y, nelem, stream):
+        self.calls.append(("mul", nelem))
+        _view(out, 1, nelem, nelem)[0][...] = _view(x, 1, nelem, nelem)[0] * _view(y, 1, nelem, nelem)[0]
+        return 0
 
     def npw_tpqrt_f64(self, V2, ldv, T, ldt, R, ldr, R0, ld0, R1, ld1, n, work, stream):
         """include/npw_b200.h: QR of [triu(R0); triu(R1)] → V2 (bottom half of the reflectors), the single n x n T, R —

@@ -43,6 +43,31 @@ def test_gloo_world(world):
     assert "DIST_OK %d" % world in outs[0]
 
 
+@pytest.mark.parametrize("world", [2, 4])
+def test_engine_over_gloo(world):
+    """The multi-rank engine itself (owner computes, transfer plan, tile exchange, failure agreement) on the host: CUDA
+    objects replaced by inert stand-ins, kernels by the NumPy C-ABI double, tiles shipped by gloo isend/irecv."""
+    port = free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port), NPW_B200_DEVICE="cpu", OMP_NUM_THREADS="1")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_dist_engine_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=400)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0, f"rank {r} failed:\n{out[-3000:]}"
+    assert "DIST_ENGINE_OK %d" % world in outs[0]
+
+
 def test_grid_shapes_and_ownership():
     assert parallel.factor_grid(1) == (1, 1)
     assert parallel.factor_grid(2) == (1, 2)

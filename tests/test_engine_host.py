@@ -1,0 +1,212 @@
+"""The REAL stream engine on the host (tests/_fakecuda.py: inert CUDA streams/events + the NumPy C-ABI double): every
+program the package ships is run through alg_wrappers -> program.start() -> job_runner.lambdapack_run — native DAG
+expansion, priorities, the fast host loop, in-place aliasing, invdiag hand-over, lower-only diagonal updates, multi-output
+stores, default (parent_fn) tiles, dead-tile reclamation — and compared with the golden outputs of the unmodified
+reference.  What this cannot see is the CUDA kernels themselves and real stream concurrency; the `-m gpu` tests do."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _fakecuda
+from numpywren_b200 import alg_wrappers, binops, job_runner, qr
+from numpywren_b200 import lambdapack as lp
+from numpywren_b200.matrix import BigMatrix
+from numpywren_b200.matrix_init import shard_matrix
+from oracle import npw_oracle as orc
+
+
+@pytest.fixture
+def engine(monkeypatch):
+    prev = qr.get_qr_semantics()
+    lib = _fakecuda.install(monkeypatch)
+    yield lib
+    qr.set_qr_semantics(prev)
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def run(program, expect=lp.PS.SUCCESS, **kw):
+    program.start()
+    out = job_runner.lambdapack_run(program, timeout=120, **kw)
+    assert program.program_status() == expect, program.exceptions
+    return out
+
+
+def cpu_matrix(key, X, b, **kw):
+    A = BigMatrix(key, shape=X.shape, shard_sizes=(b, b), device="cpu", **kw)
+    A.free()
+    shard_matrix(A, X)
+    return A
+
+
+@pytest.mark.parametrize("name", ["cholesky_64_8", "cholesky_64_16", "cholesky_60_16", "cholesky_64_32_lam"])
+@pytest.mark.parametrize("inplace", [True, False])
+def test_cholesky_golden_through_the_engine(engine, golden_dir, unique_key, name, inplace):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    n, b, lam = int(g["n"]), int(g["b"]), float(g["lambdav"])
+    A = cpu_matrix(unique_key(name), g["A"], b, lambdav=lam)
+    program, meta = alg_wrappers.cholesky(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    res = run(program, inplace=inplace)
+    assert len(res["executed_messages"]) == int(g["nnodes"]) and program.program.expanded_by == "native"
+    L = meta["outputs"][0].numpy()
+    assert rel(L, g["L"]) < 1e-12
+    assert np.array_equal(A.numpy(), g["A"] + lam * np.eye(n))              # inputs are never consumed by default
+    S = meta["intermediates"][0]
+    if inplace:
+        assert len(S.block_idxs_exist) == 0                                  # every S version was aliased in place
+    else:
+        for k in g.files:
+            if k.startswith("S_"):
+                i, j, kk = (int(x) for x in k.split("_")[1:])
+                got, ref = S.get_block(i, j, kk).numpy(), g[k].reshape(S.get_block(i, j, kk).shape)
+                if j == kk:
+                    got, ref = np.tril(got), np.tril(ref)
+                assert rel(got, ref) < 1e-12, k
+    # chol handed its by-product to the trsms of its column, and the diagonal updates used the lower-only entry point
+    kinds = [c[0] for c in engine.calls]
+    assert "potrf" in kinds and ("trsm_rlt" in kinds or n == b)
+
+
+def test_large_tiles_use_lower_only_diagonal_updates_and_consume_inputs(engine, unique_key):
+    n, b = 768, 256
+    rs = np.random.RandomState(0)
+    x = rs.randn(n, 64)
+    a = x @ x.T + n * np.eye(n)
+    A = cpu_matrix(unique_key("big"), a, b)
+    program, meta = alg_wrappers.cholesky(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    run(program, consume_inputs=True)
+    L = meta["outputs"][0].numpy()
+    assert rel(L, np.linalg.cholesky(a)) < 1e-12
+    assert any(c[0] == "syrk_lower" for c in engine.calls)
+    assert len(A.block_idxs_exist) < len(A.block_idxs)                       # input buffers were re-used
+
+
+def test_not_positive_definite_is_reported_after_the_drain(engine, unique_key):
+    bad = np.eye(64)
+    bad[50, 50] = -1.0
+    A = cpu_matrix(unique_key("bad"), bad, 16)
+    program, meta = alg_wrappers.cholesky(A)
+    program.start()
+    with pytest.raises(np.linalg.LinAlgError):
+        job_runner.lambdapack_run(program, timeout=60)
+    assert program.program_status() == lp.PS.EXCEPTION
+
+
+@pytest.mark.parametrize("name", ["gemm_64_16", "gemm_32_16"])
+@pytest.mark.parametrize("free", [False, True])
+def test_gemm_golden_through_the_engine(engine, golden_dir, unique_key, name, free):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    b = int(g["b"])
+    A = cpu_matrix(unique_key("gA"), g["A"], b)
+    B = cpu_matrix(unique_key("gB"), g["B"], b)
+    program, meta = alg_wrappers.gemm(A, B)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    res = run(program, free_intermediates=free)
+    assert len(res["executed_messages"]) == int(g["nnodes"])
+    assert rel(meta["outputs"][0].numpy(), g["C"]) < 1e-13
+    if free:
+        assert program._engine.freed_tiles > 0 and len(meta["intermediates"][0]._blocks_store) == 0
+
+
+@pytest.mark.parametrize("name", ["tsqr_256_32", "tsqr_128_16"])
+def test_tsqr_golden_through_the_engine(engine, golden_dir, unique_key, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m_, b, nlev = int(g["m"]), int(g["b"]), int(g["nlev"])
+    X = BigMatrix(unique_key("tX"), shape=(m_, b), shard_sizes=(b, b), device="cpu")
+    X.free()
+    shard_matrix(X, g["X"])
+    program, meta = alg_wrappers.tsqr(X)
+    for mm in meta["outputs"]:
+        mm.free()
+    res = run(program)
+    assert len(res["executed_messages"]) == int(g["nnodes"])
+    assert rel(meta["outputs"][0].get_block(nlev, 0).numpy(), g["R"]) < 1e-12
+
+
+def _check(g, mats, numeric=lambda name, idx: True):
+    n = 0
+    for k in g.files:
+        name = next((m for m in mats if k.startswith(m + "_")), None)
+        if name is None:
+            continue
+        idx = tuple(int(x) for x in k[len(name) + 1:].split("_"))
+        got = mats[name]._blocks_store[idx].numpy()
+        assert got.size == g[k].size
+        if numeric(name, idx):
+            assert np.abs(got.reshape(g[k].shape) - g[k]).max() <= 1e-10 * max(1.0, np.abs(g[k]).max()), k
+        n += 1
+    assert n == sum(len(m._blocks_store) for m in mats.values())
+
+
+@pytest.mark.parametrize("name", ["qr_28_7", "qr_16_8", "qr_24_8"])
+def test_qr_golden_through_the_engine(engine, golden_dir, unique_key, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    qr.set_qr_semantics("reference")
+    A = cpu_matrix(unique_key("qA"), g["X"], int(g["b"]))
+    program, meta = alg_wrappers.qr(A)
+    mats = dict(zip(["Rs", "Vs", "Ts", "Ss"], meta["outputs"] + meta["intermediates"]))
+    for m in mats.values():
+        m.free()
+    res = run(program)
+    assert len(res["executed_messages"]) == int(g["nnodes"])
+    _check(g, mats)
+
+
+@pytest.mark.parametrize("name", ["bdfac_16_4", "bdfac_16_4_trunc2", "bdfac_15_5"])
+def test_bdfac_golden_through_the_engine(engine, golden_dir, unique_key, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    qr.set_qr_semantics("reference")
+    A = cpu_matrix(unique_key("bA"), g["X"], int(g["b"]))
+    program, meta = alg_wrappers.bdfac(A, truncate=int(g["truncate"]))
+    mats = dict(zip(["L_LQ", "R_QR", "S_LQ", "S_QR", "T_QR", "V_QR", "V_LQ", "T_LQ"], meta["outputs"] + meta["intermediates"]))
+    for m in mats.values():
+        m.free()
+    # a truncated BDFAC never finishes — in the reference either: its last statement writes an output (so it counts as
+    # a terminator, 14 in all) but reads a tile the truncated loops never produce, so it never becomes ready and the
+    # terminator count stops at 13.  The runner returns when nothing is runnable; the status stays RUNNING.
+    res = run(program, expect=lp.PS.RUNNING if int(g["truncate"]) else lp.PS.SUCCESS)
+    assert len(res["executed_messages"]) == int(g["nnodes"]) and program.queue_depth() == 0
+    _check(g, mats)
+
+
+def test_qr_householder_with_reclamation_through_the_engine(engine, unique_key):
+    qr.set_qr_semantics("householder")
+    n, b = 96, 16
+    X = np.random.RandomState(4).randn(n, n)
+    A = cpu_matrix(unique_key("qh"), X, b)
+    program, meta = alg_wrappers.qr(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    run(program, free_intermediates=True)
+    Rs = meta["outputs"][0]
+    nb = n // b
+    R = np.zeros((n, n))
+    for i in range(nb):
+        for k in range(i, nb):
+            R[i * b:(i + 1) * b, k * b:(k + 1) * b] = Rs.get_block(i, k, 0).numpy()
+    assert np.abs(np.abs(R) - np.abs(np.linalg.qr(X)[1])).max() < 1e-10
+    assert program._engine.freed_tiles > 0
+
+
+def test_gemm_kloop_accumulates_in_place_through_the_engine(engine, unique_key):
+    rs = np.random.RandomState(6)
+    a, b = rs.randn(300, 260), rs.randn(260, 200)
+    A = cpu_matrix(unique_key("kA"), a, 128)
+    B = cpu_matrix(unique_key("kB"), b, 128)
+    program, meta = alg_wrappers.gemm_kloop(A, B)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    run(program)
+    Acc, Out = meta["intermediates"][0], meta["outputs"][0]
+    assert rel(Out.numpy(), a @ b) < 1e-13
+    assert len(Acc._blocks_store) == len(Out._blocks_store) == 6        # only the last version of every output tile is left
+    assert np.array_equal(A.numpy(), a) and np.array_equal(B.numpy(), b)

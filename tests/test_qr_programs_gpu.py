@@ -33,10 +33,10 @@ def semantics():
     qr.set_qr_semantics(prev)
 
 
-def run(program):
+def run(program, expect=lp.PS.SUCCESS):
     program.start()
     out = job_runner.lambdapack_run(program, timeout=300)
-    assert program.program_status() == lp.PS.SUCCESS
+    assert program.program_status() == expect
     return out
 
 
@@ -151,7 +151,9 @@ def test_bdfac_program_reference_semantics_matches_golden(golden_dir, unique_key
     mats = dict(zip(["L_LQ", "R_QR", "S_LQ", "S_QR", "T_QR", "V_QR", "V_LQ", "T_LQ"], meta["outputs"] + meta["intermediates"]))
     for m in mats.values():
         m.free()
-    res = run(program)
+    # a truncated BDFAC never reaches SUCCESS (neither does the reference's): the last statement is a terminator that can
+    # never become ready; the runner returns once nothing is runnable
+    res = run(program, expect=lp.PS.RUNNING if int(g["truncate"]) else lp.PS.SUCCESS)
     assert len(res["executed_messages"]) == int(g["nnodes"])
     # Values are compared for the first QR sweep only.  With the reference's placeholder qr_leaf (S0 - V^T S0: the last
     # row of every updated tile is exactly zero) later panels factor columns whose pivots are rounding noise, and the
