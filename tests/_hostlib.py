@@ -155,6 +155,52 @@ class HostLib:
         _view(out, 1, nelem, nelem)[0][...] = _view(x, 1, nelem, nelem)[0] * _view(y, 1, nelem, nelem)[0]
         return 0
 
+    # -- EXPERIMENTAL int8 emulation entry points, restated from include/npw_b200.h with the NumPy prototype's arithmetic
+    def npw_i8_digits_bytes(self, rows, k, ndigits):
+        return rows * k * ndigits
+
+    def npw_split_i8_f64(self, digits, exponents, X, ldx, rows, k, ndigits, stream):
+        self.calls.append(("split_i8", rows, k, ndigits))
+        x = np.array(_view(X, rows, k, ldx))
+        amax = np.abs(x).max(axis=1)
+        m, ex = np.frexp(amax)
+        e = np.where(amax > 0, np.where(m == 0.5, ex - 1, ex), 0).astype(np.int32)
+        r = x / np.exp2(e.astype(np.float64))[:, None]
+        d8 = np.ctypeslib.as_array(ctypes.cast(ctypes.c_void_p(int(digits)), ctypes.POINTER(ctypes.c_int8)),
+                                   shape=(ndigits, rows, k))
+        for p in range(ndigits):
+            r = r * (64.0 if p == 0 else 128.0)
+            q = np.rint(r)
+            d8[p] = q.astype(np.int8)
+            r = r - q
+        np.ctypeslib.as_array(ctypes.cast(ctypes.c_void_p(int(exponents)), ctypes.POINTER(ctypes.c_int32)), shape=(rows,))[...] = e
+        return 0
+
+    def npw_syrk_i8emu_f64(self, C, ldc, S, lds, xd, xe, yd, ye, m, n, k, ndigits, lower_only, stream):
+        self.calls.append(("syrk_i8emu", m, n, k, ndigits, lower_only))
+        if m % 128 or n % 64 or k % 128:
+            return -1001
+        as8 = lambda ptr, rows: np.ctypeslib.as_array(ctypes.cast(ctypes.c_void_p(int(ptr)), ctypes.POINTER(ctypes.c_int8)),
+                                                      shape=(ndigits, rows, k)).astype(np.int64)
+        as32 = lambda ptr, rows: np.ctypeslib.as_array(ctypes.cast(ctypes.c_void_p(int(ptr)), ctypes.POINTER(ctypes.c_int32)),
+                                                       shape=(rows,)).astype(np.float64)
+        X, Y = as8(xd, m), as8(yd, n)
+        acc = np.zeros((m, n))
+        for d in range(ndigits):
+            P = sum(X[p] @ Y[d - p].T for p in range(d + 1))
+            assert np.abs(P).max() < 2 ** 31
+            acc += P.astype(np.float64) * 2.0 ** -(12 + 7 * d)
+        full = np.array(_view(S, m, n, lds)) - acc * np.exp2(as32(xe, m))[:, None] * np.exp2(as32(ye, n))[None, :]
+        out = np.array(_view(S, m, n, lds))
+        if lower_only:
+            i, j = np.indices((m, n))
+            low = (j // 64) * 64 <= (i // 128) * 128 + 127
+            out[low] = full[low]
+        else:
+            out = full
+        _view(C, m, n, ldc)[...] = out
+        return 0
+
     def npw_tpqrt_f64(self, V2, ldv, T, ldt, R, ldr, R0, ld0, R1, ld1, n, work, stream):
         """include/npw_b200.h: QR of [triu(R0); triu(R1)] → V2 (bottom half of the reflectors), the single n x n T, R —
         restated here with the general LAPACK QR of the explicit stack, the way the CUDA entry point computes it."""

@@ -210,3 +210,28 @@ def test_gemm_kloop_accumulates_in_place_through_the_engine(engine, unique_key):
     assert rel(Out.numpy(), a @ b) < 1e-13
     assert len(Acc._blocks_store) == len(Out._blocks_store) == 6        # only the last version of every output tile is left
     assert np.array_equal(A.numpy(), a) and np.array_equal(B.numpy(), b)
+
+
+@pytest.mark.parametrize("digits,tol", [(5, 1e-9), (6, 1e-11), (8, 1e-14)])
+def test_experimental_i8emu_mode_through_the_engine(engine, unique_key, monkeypatch, digits, tol):
+    """NPW_B200_SYRK=i8emu: the engine extracts a panel tile's int8 digits once, reuses them for every syrk of its block
+    row / column, releases them after the last one, and the factor stays within the accuracy the prototype predicts.
+    (The C-ABI double restates npw_split_i8_f64 / npw_syrk_i8emu_f64 from the header; the tcgen05 kernel itself has
+    never run.)"""
+    monkeypatch.setenv("NPW_B200_SYRK", "i8emu")
+    monkeypatch.setenv("NPW_B200_I8_DIGITS", str(digits))
+    n, b = 640, 128
+    nb = n // b
+    a = np.block([[orc.spd_tile(j, k, b, n, width=64) for k in range(nb)] for j in range(nb)])
+    A = cpu_matrix(unique_key("i8"), a, b)
+    program, meta = alg_wrappers.cholesky(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    run(program)
+    L = meta["outputs"][0].numpy()
+    assert rel(L, np.linalg.cholesky(a)) < tol
+    kinds = [c[0] for c in engine.calls]
+    assert kinds.count("split_i8") == nb * (nb - 1) // 2          # once per panel tile O[j,i], j > i
+    assert kinds.count("syrk_i8emu") == (nb - 1) * nb * (nb + 1) // 6 and "syrk" not in kinds and "syrk_lower" not in kinds
+    assert any(c[0] == "syrk_i8emu" and c[5] == 1 for c in engine.calls)   # diagonal updates: lower-only
+    assert len(program._engine._digits) == 0                      # every digit cache entry was released
