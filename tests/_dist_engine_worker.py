@@ -92,6 +92,20 @@ def main():
         C = binops.gemm(None, GA, GB).numpy()
         assert np.linalg.norm(C - ga @ gb) / np.linalg.norm(ga @ gb) < 1e-13
 
+        # ---- TSQR: leaves live on rank j mod world, only the R factors of the tree cross ranks
+        gt = np.load(os.path.join(ROOT, "tests", "golden", "tsqr_256_32.npz"))
+        Xt = BigMatrix("de_tsqr", shape=(256, 32), shard_sizes=(32, 32), device="cpu")
+        program, meta = alg_wrappers.tsqr(Xt)          # the wrapper attaches the placement before tiles are stored
+        shard_matrix(Xt, gt["X"])
+        assert sorted(Xt.block_idxs_exist) == [(j, 0) for j in range(8) if j % grid.world == grid.rank]
+        program.start()
+        job_runner.lambdapack_run(program, timeout=120)
+        assert program.program_status() == lp.PS.SUCCESS
+        Rt = meta["outputs"][0]
+        nlev = int(gt["nlev"])
+        Rfin = gather_tile(Rt, (nlev, 0), grid)
+        assert np.linalg.norm(Rfin - gt["R"]) / np.linalg.norm(gt["R"]) < 1e-12
+
         # ---- a failure on one rank is a failure on all
         bad = np.eye(32)
         bad[20, 20] = -1.0
