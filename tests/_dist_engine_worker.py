@@ -45,8 +45,10 @@ def main():
         A = BigMatrix("de_chol", shape=(64, 64), shard_sizes=(8, 8), device="cpu")
         shard_matrix(A, g["A"])
         program, meta = alg_wrappers.cholesky(A)
+        plan_s = job_runner.prepare(program, streams=8, consume_inputs=True)   # as bench.py does before its timed region
+        assert plan_s >= 0 and program._engine.comm is not None and program._engine.n_streams == 8
         program.start()
-        job_runner.lambdapack_run(program, timeout=120)
+        job_runner.lambdapack_run(program, timeout=120, streams=8, consume_inputs=True)
         assert program.program_status() == lp.PS.SUCCESS
         L = meta["outputs"][0].numpy()
         assert np.linalg.norm(L - g["L"]) / np.linalg.norm(g["L"]) < 1e-12

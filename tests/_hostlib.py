@@ -150,6 +150,16 @@ class HostLib:
         ctypes.cast(ctypes.c_void_p(int(info)), ctypes.POINTER(ctypes.c_int32))[0] = code
         return 0
 
+    def npw_fill_random_f64(self, A, lda, rows, cols, seed, row0, col0, stream):
+        """Any reproducible U(-1, 1) fill keyed by (seed, global row, global column) will do for host-logic tests."""
+        self.calls.append(("fill_random", rows, cols))
+        i, j = np.indices((rows, cols), dtype=np.uint64)
+        x = (i + np.uint64(row0)) * np.uint64(0x9E3779B97F4A7C15) + (j + np.uint64(col0)) * np.uint64(0xBF58476D1CE4E5B9) \
+            + np.uint64(seed)
+        x ^= x >> np.uint64(30); x *= np.uint64(0xBF58476D1CE4E5B9); x ^= x >> np.uint64(27)
+        _view(A, rows, cols, lda)[...] = (x >> np.uint64(11)).astype(np.float64) / float(1 << 53) * 2.0 - 1.0
+        return 0
+
     def npw_mul_f64(self, out, x, y, nelem, stream):
         self.calls.append(("mul", nelem))
         _view(out, 1, nelem, nelem)[0][...] = _view(x, 1, nelem, nelem)[0] * _view(y, 1, nelem, nelem)[0]

@@ -235,3 +235,17 @@ def test_experimental_i8emu_mode_through_the_engine(engine, unique_key, monkeypa
     assert kinds.count("syrk_i8emu") == (nb - 1) * nb * (nb + 1) // 6 and "syrk" not in kinds and "syrk_lower" not in kinds
     assert any(c[0] == "syrk_i8emu" and c[5] == 1 for c in engine.calls)   # diagonal updates: lower-only
     assert len(program._engine._digits) == 0                      # every digit cache entry was released
+
+
+def test_bench_gpu_step_flow_on_the_host(engine, monkeypatch):
+    """bench.py's timed step (resident input -> cholesky() -> prepare -> start -> lambdapack_run) with the host harness:
+    the flow the driver runs at round end, minus the device."""
+    import bench
+    monkeypatch.setattr(bench.torch.cuda, "synchronize", lambda device=None: None)
+    wl = bench.Workload(512, 128, torch.device("cpu"))
+    ms, launches, A, program, meta = bench.gpu_step(wl, streams=4)
+    assert program.program_status() == lp.PS.SUCCESS and launches > 0
+    assert getattr(program, "_engine", None) is not None and program._engine.n_streams == 4
+    resid = bench.residual_check(wl, meta["outputs"][0], [(0, 0), (3, 0), (3, 3), (2, 1)])
+    assert resid < 1e-13
+    bench.free_all(A, meta)
