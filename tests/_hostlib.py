@@ -141,11 +141,10 @@ class HostLib:
         self.calls.append(("potrf", n))
         a = np.tril(np.array(_view(A, n, n, lda)))
         a = a + np.tril(a, -1).T
-        code = 0
-        try:
-            l = np.linalg.cholesky(a)
-        except np.linalg.LinAlgError:
-            l, code = np.eye(n), 1          # the CUDA kernel leaves NaNs; any finite stand-in keeps later host calls alive
+        l, code = scipy.linalg.lapack.dpotrf(a, lower=1)          # info = order of the first non-positive leading minor
+        l = np.tril(l)
+        if code != 0:
+            l = np.eye(n)                   # the CUDA kernel leaves NaNs; any finite stand-in keeps later host calls alive
         _view(L_out, n, n, ldl)[...] = l
         ctypes.cast(ctypes.c_void_p(int(info)), ctypes.POINTER(ctypes.c_int32))[0] = code
         return 0

@@ -15,7 +15,8 @@ TOL = 1e-10
 
 
 def dev(a, cuda_device):
-    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda_device)
+    # np.array(...) copies: on the host harness (conftest NPW_B200_HOST_HARNESS) .to("cpu") would alias the ndarray
+    return torch.from_numpy(np.array(a, dtype=np.float64, order="C")).to(cuda_device)
 
 
 def rel(got, want):
