@@ -249,3 +249,58 @@ def test_bench_gpu_step_flow_on_the_host(engine, monkeypatch):
     resid = bench.residual_check(wl, meta["outputs"][0], [(0, 0), (3, 0), (3, 3), (2, 1)])
     assert resid < 1e-13
     bench.free_all(A, meta)
+
+
+def test_duplicate_and_premature_messages_are_harmless(engine, golden_dir, unique_key):
+    """Reference tests/test_failures.py:24-120 re-delivers random task messages and expects the same factor: a finished
+    node is skipped (repeated_finish), a node whose parents have not all finished is not run early (not_ready) — which
+    matters doubly here because finished inputs may already have been overwritten in place."""
+    import random
+    g = np.load(os.path.join(golden_dir, "cholesky_64_8.npz"))
+    A = cpu_matrix(unique_key("dup"), g["A"], 8)
+    program, meta = alg_wrappers.cholesky(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    job_runner.prepare(program)
+    nodes = program.program.nodes
+    rnd = random.Random(0)
+    program.start()
+    orig = job_runner.TileEngine.run_node
+    injected = [0]
+
+    def run_and_inject(self, node):
+        orig(self, node)
+        for _ in range(2):                                   # after every task, re-deliver two random messages
+            victim = nodes[rnd.randrange(len(nodes))]
+            program._enqueue(victim.expr_idx, victim.var_values, priority=rnd.randrange(100))
+            injected[0] += 1
+    job_runner.TileEngine.run_node = run_and_inject
+    try:
+        res = job_runner.lambdapack_run(program, timeout=120)
+    finally:
+        job_runner.TileEngine.run_node = orig
+    assert program.program_status() == lp.PS.SUCCESS
+    assert len(res["executed_messages"]) == len(nodes)                       # every node ran exactly once
+    assert program._get("repeated_finish") + program._get("not_ready") == injected[0] - program.queue_depth() > 0
+    assert rel(meta["outputs"][0].numpy(), g["L"]) < 1e-12
+
+
+def test_several_runner_threads_on_one_program(engine, golden_dir, unique_key):
+    """Reference tests/test_alg_correctness.py:160-187 / test_job_runner.py:64-91 submit several lambdapack_run workers for
+    one program.  Here workers are threads of one process sharing the engine: together they run every node exactly once."""
+    import concurrent.futures as fs
+    g = np.load(os.path.join(golden_dir, "cholesky_64_8.npz"))
+    A = cpu_matrix(unique_key("thr"), g["A"], 8)
+    program, meta = alg_wrappers.cholesky(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    job_runner.prepare(program)
+    program.start()
+    with fs.ThreadPoolExecutor(3) as ex:
+        futs = [ex.submit(job_runner.lambdapack_run, program, timeout=120) for _ in range(3)]
+        outs = [f.result() for f in futs]
+    program.wait()
+    assert program.program_status() == lp.PS.SUCCESS
+    assert sum(len(o["executed_messages"]) for o in outs) == len(program.program.nodes)
+    assert rel(meta["outputs"][0].numpy(), g["L"]) < 1e-12
+    assert program.get_up() == 0
