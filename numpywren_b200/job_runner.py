@@ -124,8 +124,10 @@ class TileEngine:
         self.skip_upper = os.environ.get("NPW_B200_SKIP_UPPER", "1") != "0"
         # dead-tile reclamation (opt-in): an SSA intermediate is dropped from the HBM store as soon as its last reader
         # has been enqueued.  The reference keeps every version in S3 for ever; in HBM the QR / BDFAC / GEMM programs'
-        # intermediates would otherwise outgrow the device (GEMM Temp: M*N*K tiles).  Single-GPU engine only.
-        self.free_intermediates = free_intermediates and comm is None
+        # intermediates would otherwise outgrow the device (GEMM Temp: M*N*K tiles).  On several GPUs a rank counts the
+        # readers it executes itself: copies to other ranks are enqueued right after the producing node and keep their
+        # own reference to the buffer (record_stream / pending send), so they do not pin the store entry.
+        self.free_intermediates = free_intermediates
         self._keep_mats = {id(self.compiled.scope[n]) for n in list(self.compiled.inputs) + list(self.compiled.outputs)
                            if n in self.compiled.scope}
         self._reads_left: Dict[Any, int] = {}
@@ -403,7 +405,11 @@ class TileEngine:
             key = keys[j]
             left = self._reads_left.get(key)
             if left is None:
-                left = self.compiled.num_readers(m, idx)
+                if self.comm is None:
+                    left = self.compiled.num_readers(m, idx)
+                else:
+                    mine = self.comm.rank
+                    left = sum(1 for r in self.compiled._readers.get(key, ()) if self.comm.plan.exec_rank[r] == mine)
             left -= 1
             self._reads_left[key] = left
             if left <= 0 and key not in written:

@@ -65,8 +65,11 @@ def main():
         shard_matrix(Aq, X)
         program, meta = alg_wrappers.qr(Aq)
         program.start()
-        job_runner.lambdapack_run(program, timeout=120)
+        job_runner.lambdapack_run(program, timeout=120, free_intermediates=True)   # dead S versions are dropped per rank
         assert program.program_status() == lp.PS.SUCCESS
+        freed = torch.tensor([program._engine.freed_tiles], dtype=torch.int64)
+        dist.all_reduce(freed)
+        assert int(freed.item()) > 0
         Rs = meta["outputs"][0]
         R = np.zeros((n, n))
         for i in range(nb):
