@@ -57,8 +57,17 @@ ES = EdgeStatus
 PS = ProgramStatus
 
 
+_NBYTES_CACHE = {}
+
+
 def _nbytes(matrix):
-    return int(np.prod(matrix.shard_sizes)) * np.dtype(matrix.dtype).itemsize
+    """Bytes of one full tile of ``matrix`` (the reference's read/write counters, lambdapack.py:234,293); cached per
+    (shard sizes, dtype) — the engine asks once per tile read or written."""
+    key = (tuple(matrix.shard_sizes), str(matrix.dtype))
+    v = _NBYTES_CACHE.get(key)
+    if v is None:
+        v = _NBYTES_CACHE[key] = int(np.prod(matrix.shard_sizes)) * np.dtype(matrix.dtype).itemsize
+    return v
 
 
 class RemoteInstruction(object):
