@@ -154,3 +154,29 @@ def run(s, kblocks, seed):
 def test_barrier_protocol_has_no_deadlock_and_no_hazard(s, kblocks):
     for seed in range(6):
         run(s, kblocks, seed)
+
+
+def test_hand_packed_umma_descriptors_equal_cutlass_bitfields(tmp_path):
+    """csrc/npw_ozaki_i8.cu packs the tcgen05 shared-memory / instruction descriptors by hand; the vendored CUTLASS headers
+    define the same fields as bitfield structs.  Compile a host program that builds both and compare."""
+    import os
+    import shutil
+    import site
+    import subprocess
+    inc = None
+    for sp in site.getsitepackages():
+        cand = os.path.join(sp, "flashinfer", "data", "cutlass", "include")
+        if os.path.exists(os.path.join(cand, "cute", "arch", "mma_sm100_desc.hpp")):
+            inc = cand
+    if inc is None or shutil.which("nvcc") is None:
+        pytest.skip("CUTLASS headers or nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "umma_desc_check")
+    subprocess.run(["nvcc", "-std=c++17", "-w", "-I" + inc, "-o", exe, os.path.join(root, "tools", "umma_desc_check.cu")],
+                   check=True, capture_output=True, timeout=300)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stdout
+    # and the kernel source really uses the same packing as the checked copy
+    src = open(os.path.join(root, "numpywren_b200", "csrc", "npw_ozaki_i8.cu")).read()
+    for frag in ("<< 16;", "(1024 >> 4) << 32;", "<< 46;", "<< 61;", "(2u << 4) | (1u << 7) | (1u << 10)"):
+        assert frag in src
