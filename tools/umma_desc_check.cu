@@ -5,6 +5,9 @@
 #include <cstdint>
 #include <cute/arch/mma_sm100_desc.hpp>
 #include <cute/numeric/numeric_types.hpp>
+#include <cute/layout.hpp>
+#include <cute/swizzle.hpp>
+#include <cute/swizzle_layout.hpp>
 static uint64_t my_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFFu);
@@ -30,5 +33,13 @@ int main() {
   printf("cutlass smem desc %016llx\nmine              %016llx\n", (unsigned long long)d.desc_, (unsigned long long)my_desc(addr));
   auto id = UMMA::make_instr_desc<int8_t, int8_t, int32_t, 128, 64, UMMA::Major::K, UMMA::Major::K>();
   printf("cutlass idesc %08x\nmine          %08x\n", (unsigned)uint32_t(id), my_idesc(128, 64));
-  return (d.desc_ == my_desc(addr) && uint32_t(id) == my_idesc(128, 64)) ? 0 : 1;
+  // the byte placement tools/tcgen05_i8_probe.cu writes by hand (and TMA's SWIZZLE_128B produces) against CuTe's K-major
+  // SW128 atom for 8-bit elements: Swizzle<3,4,3> o (8 rows x 128 bytes, row stride 128)
+  auto atom = composition(Swizzle<3, 4, 3>{}, Layout<Shape<_8, _128>, Stride<_128, _1>>{});
+  int bad = 0;
+  for (int r = 0; r < 8; ++r)
+    for (int k = 0; k < 128; ++k)
+      if (r * 128 + (((k / 16) ^ (r % 8)) * 16) + k % 16 != int(atom(r, k))) ++bad;
+  printf("swizzle formula mismatches: %d\n", bad);
+  return (d.desc_ == my_desc(addr) && uint32_t(id) == my_idesc(128, 64) && bad == 0) ? 0 : 1;
 }
