@@ -22,6 +22,7 @@ Program state (node status, edge sums, terminator count, counters) still goes th
 from __future__ import annotations
 
 import os
+import threading
 import time
 import traceback
 from typing import Any, Dict, List, Optional, Tuple
@@ -117,6 +118,7 @@ class TileEngine:
         self.infos: List[Tuple[ExpandedNode, torch.Tensor]] = []
         self.timeline: List[Tuple[ExpandedNode, torch.cuda.Event, torch.cuda.Event, int]] = []
         self.launched = 0
+        self._issue_lock = threading.RLock()
         self.input_names = set(self.compiled.inputs)
         self._input_mats = {id(self.compiled.scope[n]) for n in self.input_names if n in self.compiled.scope}
         self._prio: Optional[List[int]] = None
@@ -258,6 +260,12 @@ class TileEngine:
 
     # ------------------------------------------------------------------ one node
     def run_node(self, node: ExpandedNode):
+        """Enqueue one tile task.  Several runner threads may share the engine (the reference's tests start several
+        workers per program): issuing is serialised here — it is host work only, the kernels run asynchronously."""
+        with self._issue_lock:
+            self._run_node(node)
+
+    def _run_node(self, node: ExpandedNode):
         first_m = node.reads[0][0] if node.reads else node.writes[0][0]
         self._ensure_device(first_m.device)
         stream = self._stream_for(node)
@@ -425,11 +433,12 @@ class TileEngine:
         if self.device is not None:
             torch.cuda.synchronize(self.device)
         bad = []
-        for node, info in self.infos:
+        with self._issue_lock:
+            infos, self.infos = self.infos, []
+        for node, info in infos:
             code = int(info.item())
             if code != 0:
                 bad.append((node, code))
-        self.infos = []
         if self.comm is not None:
             # every rank must agree on failure: share the smallest failing node id (or "none")
             from . import parallel
