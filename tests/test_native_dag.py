@@ -155,3 +155,88 @@ def test_header_and_library_agree():
     lib = ctypes.CDLL(_dag_native._LIB_PATH)
     for n in names:
         getattr(lib, n)
+
+
+# --------------------------------------------------------------------------- differential test on random programs
+def _random_program(rnd):
+    """A random LambdaPACK program: loop nests with affine / non-affine bounds, scoped scalar assignments, a static if,
+    and remote calls writing tiles whose index (all loop variables + a unique tag) keeps the program SSA."""
+    lines = ["def P(A: BigMatrix, B: BigMatrix, N: int, M: int):"]
+    tag = [0]
+
+    def expr(names, depth=0):
+        r = rnd.random()
+        if depth > 2 or r < 0.35:
+            return rnd.choice(names + [str(rnd.randint(0, 6))])
+        op = rnd.choice(["+", "-", "*", "//", "%", "**", "+", "-"])
+        a, b = expr(names, depth + 1), expr(names, depth + 1)
+        if op in ("//", "%"):
+            b = str(rnd.randint(1, 5)) if rnd.random() < 0.5 else "(%s %% 4 + %d)" % (b, rnd.randint(1, 3))
+        if op == "**":
+            a, b = "(%s %% 5)" % a, str(rnd.randint(0, 3))
+        return "(%s %s %s)" % (a, op, b)
+
+    def body(indent, loop_vars, depth, names):
+        names = list(names)                                   # assignments are scoped to the enclosing block
+        pad = "    " * indent
+        for _ in range(rnd.randint(1, 2) if depth == 0 else 1):
+            if rnd.random() < 0.5:
+                tag[0] += 1
+                v = "t%d" % tag[0]
+                lines.append("%s%s = %s" % (pad, v, expr(names)))
+                names.append(v)
+            if depth < 3 and rnd.random() < 0.8:
+                lv = "i%d_%d" % (depth, tag[0])
+                tag[0] += 1
+                lo = rnd.choice(["0", "1", str(rnd.randint(-2, 2)), loop_vars[-1] if loop_vars else "0"])
+                hi = rnd.choice(["N", "M", "N + 1", "ceiling(log(N + 1) / log(2))", "(N * M) % 5 + 1", "floor(M / 2) + 2"])
+                step = rnd.choice(["1", "1", "2", "2 ** (%s %% 3)" % (loop_vars[-1] if loop_vars else "1")])
+                lines.append("%sfor %s in range(%s, %s, %s):" % (pad, lv, lo, hi, step))
+                body(indent + 1, loop_vars + [lv], depth + 1, names + [lv])
+            else:
+                def call():
+                    tag[0] += 1
+                    idx = ", ".join(["%s + 40" % v for v in loop_vars] + ["0"] * (3 - len(loop_vars)) + [str(tag[0])])
+                    rd = ", ".join(["(%s) %% 97" % expr(names) for _ in range(2)])
+                    return "B[%s] = identity(A[%s])" % (idx, rd)
+                if rnd.random() < 0.3:
+                    lines.append("%sif %s < %s:" % (pad, expr(names), expr(names)))
+                    lines.append("%s    %s" % (pad, call()))
+                    lines.append("%selse:" % pad)
+                    lines.append("%s    %s" % (pad, call()))
+                else:
+                    lines.append("%s%s" % (pad, call()))
+
+    body(1, [], 0, ["N", "M"])
+    return "\n".join(lines) + "\n"
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_random_programs_expand_identically(seed):
+    import random
+    if _dag_native.load() is None:
+        pytest.skip("libnpw_dag.so is not built")
+    rnd = random.Random(seed)
+    src = _random_program(rnd)
+    args = (dummy(2), dummy(4), rnd.randint(2, 9), rnd.randint(2, 7))
+    # the Python expander is the specification: whatever it does (nodes or an exception), the default path must do too
+    os.environ["NPW_B200_NATIVE_DAG"] = "0"
+    saved = (_dag_native._lib, _dag_native._load_failed)
+    _dag_native._lib, _dag_native._load_failed = None, False
+    try:
+        p_py = compiler.lpcompile(src)(*args)
+        try:
+            p_py.nodes
+            err = None
+        except Exception as e:      # e.g. negative exponent -> float index, huge ranges are not generated
+            err = type(e)
+    finally:
+        os.environ.pop("NPW_B200_NATIVE_DAG")
+        _dag_native._lib, _dag_native._load_failed = saved
+    p_nat = compiler.lpcompile(src)(*args)
+    if err is not None:
+        with pytest.raises(err):
+            p_nat.nodes
+        return
+    p_nat.nodes
+    same(p_nat, p_py)
