@@ -519,15 +519,33 @@ def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, 
     program._defer_success = True
     nodes = program.program.nodes
     executed, refs = [], []
+    if eng.comm is not None:
+        with program._lock:
+            if program._runner_active > 1:
+                # the tile exchange pairs the k-th send with the k-th receive of every (src, dst): all ranks must walk
+                # the DAG in the same order, which several runner threads on one rank cannot guarantee
+                program._runner_active -= 1
+                program.decr_up(1)
+                raise RuntimeError("lambdapack_run: one runner thread per rank when the program is sharded over GPUs")
+    counted = True
+    next_node = None      # eager=True: post_op hands one ready child straight back to this runner (reference :113-139)
     try:
         while program.program_status() == lp.PS.RUNNING:
             if time.time() - lambda_start > timeout:
+                if next_node is not None:      # not run: back to the queue, it is READY
+                    prio = getattr(program, "_prio_by_nid", None)
+                    program._enqueue_node(next_node, prio[next_node.nid] if prio is not None else 0)
+                    next_node = None
                 break
-            item = program._dequeue_item()
-            if item is None:
-                break
-            expr_idx, frozen, nid = item
-            node = nodes[nid] if nid is not None else program.program.node(expr_idx, dict(frozen))
+            if next_node is not None:
+                node, next_node = next_node, None
+                expr_idx = node.expr_idx
+            else:
+                item = program._dequeue_item()
+                if item is None:
+                    break
+                expr_idx, frozen, nid = item
+                node = nodes[nid] if nid is not None else program.program.node(expr_idx, dict(frozen))
             var_values = node.var_values
             status = program.node_status_of(node)
             if status == lp.NS.FINISHED:
@@ -550,8 +568,10 @@ def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, 
                         comm.after_node(node, eng)
                 else:
                     program.incr_repeated_post_op()
-                program.post_op_node(node, lp.PS.SUCCESS)
+                nxt, _ = program.post_op_node(node, lp.PS.SUCCESS)
                 program.set_node_status_of(node, lp.NS.FINISHED)
+                if nxt is not None:
+                    next_node = program.program.node(nxt[0], nxt[1])
             except Exception:
                 tb = traceback.format_exc()
                 program.handle_exception("EXCEPTION", tb=tb, expr_idx=expr_idx, var_values=var_values)
@@ -565,13 +585,20 @@ def lambdapack_run(program, pipeline_width=5, msg_vis_timeout=60, cache_size=5, 
             raise np.linalg.LinAlgError(
                 "Matrix is not positive definite (tile task {0}{1}: leading minor {2})".format(
                     node.call.compute_name, node.var_values, code))
+        # Only the LAST runner to leave may publish SUCCESS: its finish() (device drained, chol info codes checked)
+        # happens after every other runner's last issue, because a runner leaves the count only here, after its own
+        # finish().  A runner that drained early and then sees the flag set by a peer must not publish for it.
         with program._lock:
-            if getattr(program, "_all_terminators_done", False) and program._status == lp.PS.RUNNING:
+            program._runner_active -= 1
+            counted = False
+            if program._runner_active == 0 and getattr(program, "_all_terminators_done", False) \
+                    and program._status == lp.PS.RUNNING:
                 program._status = lp.PS.SUCCESS
     finally:
         program.decr_up(1)
-        with program._lock:
-            program._runner_active -= 1
+        if counted:
+            with program._lock:
+                program._runner_active -= 1
     lambda_stop = time.time()
     return {"up_time": [lambda_start, lambda_stop],
             "exec_time": calculate_busy_time([[lambda_start, lambda_stop]]) if executed else [],

@@ -302,6 +302,13 @@ class BigMatrix(object):
         self._blocks_store[block_idx] = tile
         self._entry["ready"][block_idx] = ev
 
+    def wait_uploads(self):
+        """Block until every ``put_block(..., non_blocking=True)`` upload of this matrix has landed in HBM."""
+        ready = self._entry["ready"]
+        for ev in list(ready.values()):
+            ev.synchronize()
+        ready.clear()
+
     # ---- write-through host mirror (the analogue of "the PUT made the tile durable"): every tile stored into this
     # matrix is also copied to pinned host memory on the download stream, overlapping the rest of the program.
     def mirror_to_host(self, buffers=None):
@@ -384,8 +391,13 @@ class BigMatrix(object):
     async def get_block_async(self, loop, *block_idx):
         return self.get_block(*block_idx)
 
-    def put_block(self, block, *block_idx):
-        """Store a copy of ``block`` (tensor or ndarray) as tile ``block_idx`` (reference matrix.py:312-361)."""
+    def put_block(self, block, *block_idx, non_blocking=False):
+        """Store a copy of ``block`` (tensor or ndarray) as tile ``block_idx`` (reference matrix.py:312-361).
+
+        Like the reference's synchronous PUT, the copy is complete when this returns: the caller may reuse ``block``.
+        ``non_blocking=True`` (an extension; needs a pinned, contiguous host tensor, else it is ignored) starts the
+        host-to-HBM copy on the matrix's upload stream and returns at once — consumers wait on the tile's event, and the
+        caller must leave ``block`` untouched until ``wait_uploads()`` (or the program that reads the tile) has finished."""
         block_idx = tuple(int(i) for i in block_idx)
         current_shape = self.block_shape(*block_idx)
         shape = tuple(block.shape)
@@ -397,8 +409,8 @@ class BigMatrix(object):
             raise Exception("{2} Incompatible block size: {0} vs {1}".format(shape, current_shape, self))
         if not self._is_local(block_idx):
             return None   # SPMD: every rank issues the same put, only the tile's owner stores it
-        if (isinstance(block, torch.Tensor) and not block.is_cuda and block.is_pinned() and block.is_contiguous()
-                and self.device.type == "cuda"):
+        if (non_blocking and isinstance(block, torch.Tensor) and not block.is_cuda and block.is_pinned()
+                and block.is_contiguous() and self.device.type == "cuda"):
             self._upload_async(block.reshape(current_shape), block_idx)   # overlapped H2D, consumers wait on its event
         else:
             self._entry["ready"].pop(block_idx, None)

@@ -185,6 +185,18 @@ def _tile_shape(m, idx):
     return tuple(m.block_shape(*idx))
 
 
+def _wait_upload(m, idx, ref, engine_event, stream):
+    """An input tile stored by ``put_block(..., non_blocking=True)`` from pinned host memory may still be arriving on the
+    matrix's upload stream: a transfer of such a tile (no engine event yet) must be ordered after that copy, exactly like
+    ``TileEngine._read`` does for local consumers."""
+    if ref is None or engine_event is not None or not hasattr(m, "_ready_event"):
+        return
+    up = m._ready_event(*m.true_block_idx(*idx))
+    if up is not None:
+        stream.wait_event(up)
+        ref.record_stream(stream)
+
+
 class TileExchange:
     """Posts the planned sends/recvs with torch.distributed P2P (NCCL over NVLink) as the engine walks the DAG."""
 
@@ -211,6 +223,7 @@ class TileExchange:
                     tile = ref
                 ev = engine.tile_event.get(key)
                 stream = ev[1] if ev is not None else torch.cuda.current_stream()
+                _wait_upload(m, idx, ref, ev, stream)
                 with torch.cuda.stream(stream):
                     # issued on the producer's stream: NCCL orders the send after the kernel that wrote the tile
                     self.pending_sends.append((dist.isend(tile.contiguous(), dst), tile))
@@ -291,6 +304,12 @@ class SymmTileExchange(TileExchange):
         super().__init__(compiled, grid)
         self.device = device
         self.slot, self.slot_elems, self.max_slots = self.plan.assign_inbox_slots()
+        # inbox slots are typed and sized for fp64 tiles (the only dtype the C-ABI kernels compute in)
+        for lst in list(self.plan.before_node.values()) + list(self.plan.after_node.values()):
+            for _key, m, _idx, _src, _dst in lst:
+                if m.torch_dtype != torch.float64:
+                    raise TypeError("SymmTileExchange moves float64 tiles only; {0} is {1} (use NPW_B200_EXCHANGE=nccl)".format(
+                        m.key, m.torch_dtype))
         self.inbox, self.hdl = _symmetric_inbox(max(1, self.max_slots) * self.slot_elems * 8, device)
         self.send_streams: Dict[int, torch.cuda.Stream] = {}
         self.recv_streams: Dict[int, torch.cuda.Stream] = {}
@@ -315,6 +334,7 @@ class SymmTileExchange(TileExchange):
                     s.wait_event(ev[0])
                 else:
                     s.wait_stream(torch.cuda.current_stream(self.device))
+                _wait_upload(m, idx, ref, ev, s)
                 with torch.cuda.stream(s):
                     peer = self.hdl.get_buffer(dst, shape, torch.float64, off)
                     peer.copy_(tile.reshape(shape), non_blocking=True)
@@ -461,7 +481,7 @@ def bench_main(args, metric, unit, workload):
         e0.record()
         A = BigMatrix(f"bench_e2e_{i}", shape=(n, n), shard_sizes=(b, b), device=device)
         for (j, k) in sorted(host_in, key=lambda jk: (jk[1], jk[0])):
-            A.put_block(host_in[(j, k)], j, k)
+            A.put_block(host_in[(j, k)], j, k, non_blocking=True)
         program, meta = cholesky(A)
         O = meta["outputs"][0]
         O.mirror_to_host(host_out)

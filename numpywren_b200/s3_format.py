@@ -28,9 +28,28 @@ def encode_dtype(dtype) -> str:
     return base64.b64encode(pickle.dumps(dtype)).decode("utf-8")
 
 
+class _DtypeUnpickler(pickle.Unpickler):
+    """The header's ``dtype`` field is a pickle (reference matrix.py:547-555) read from a directory synced from an
+    external deployment: resolve nothing but NumPy's dtype constructor and scalar type classes, so that a crafted
+    header cannot name an arbitrary callable."""
+
+    def find_class(self, module, name):
+        if module in ("numpy", "numpy.core.multiarray", "numpy._core.multiarray", "numpy.core.numerictypes",
+                      "numpy._core.numerictypes"):
+            obj = getattr(np, name, None)
+            if name == "dtype" and obj is np.dtype:
+                return obj
+            if isinstance(obj, type) and issubclass(obj, np.generic):
+                return obj
+        raise pickle.UnpicklingError("header dtype field names {0}.{1}: only NumPy dtypes are accepted".format(module, name))
+
+
 def decode_dtype(enc: str):
-    """matrix.py:552-555."""
-    return pickle.loads(base64.b64decode(enc))
+    """matrix.py:552-555, restricted to NumPy dtypes (np.float64 the class, or an np.dtype instance)."""
+    obj = _DtypeUnpickler(io.BytesIO(base64.b64decode(enc))).load()
+    if not (isinstance(obj, np.dtype) or (isinstance(obj, type) and issubclass(obj, np.generic))):
+        raise pickle.UnpicklingError("header dtype field does not decode to a NumPy dtype")
+    return obj
 
 
 def tile_object_name(bigm, block_idx) -> str:

@@ -102,9 +102,10 @@ def import_reference():
         STORE[(self.key, tuple(int(x) for x in block_idx))] = np.array(block, copy=True)
         return None
 
+    orig = dict(get_block_async=matrix.BigMatrix.get_block_async, put_block_async=matrix.BigMatrix.put_block_async)
     matrix.BigMatrix.get_block_async = get_block_async
     matrix.BigMatrix.put_block_async = put_block_async
-    return dict(algs=algs, compiler=compiler, frontend=frontend, kernels=kernels, lp=lambdapack, matrix=matrix,
+    return dict(orig=orig, algs=algs, compiler=compiler, frontend=frontend, kernels=kernels, lp=lambdapack, matrix=matrix,
                 matrix_utils=matrix_utils, STORE=STORE)
 
 
@@ -421,9 +422,70 @@ def structure_counts(ref):
     return out
 
 
+def golden_s3_format(ref):
+    """Objects the UNMODIFIED reference writes for a BigMatrix: the header (matrix.py:535-545, through boto3's
+    put_object) and every tile (put_block_async -> __shard_idx_to_key__ -> __save_matrix_to_s3__, matrix.py:318-361,
+    457-464, 519-533, through aiobotocore's put_object).  boto3 / aiobotocore are replaced by recorders, so what is kept
+    is exactly the (Key, Body) pairs the reference would have sent to S3.  -> tests/golden/s3_format.json"""
+    import base64
+    import boto3
+    import aiobotocore
+    matrix = ref["matrix"]
+    objects = {}
+
+    class SyncClient:
+        def put_object(self, Key, Bucket, Body, ACL=None):
+            objects[Key] = Body.encode("utf-8") if isinstance(Body, str) else bytes(Body)
+
+    class AsyncClient:
+        async def __aenter__(self):
+            return self
+
+        async def __aexit__(self, *a):
+            return False
+
+        async def put_object(self, Key, Bucket, Body, ACL=None):
+            objects[Key] = bytes(Body)
+
+    class Session:
+        def create_client(self, *a, **k):
+            return AsyncClient()
+    boto3.client = lambda *a, **k: SyncClient()
+    aiobotocore.get_session = lambda loop=None: Session()
+    patched = matrix.BigMatrix.put_block_async
+    matrix.BigMatrix.put_block_async = ref["orig"]["put_block_async"]
+    out = {}
+    try:
+        cases = [("fmt2d", (10, 7), (4, 4), np.float64, {}),                       # ragged in both axes
+                 ("fmt3d", (3, 8, 6), (1, 4, 4), np.float64, {}),                  # the Cholesky intermediate's layout
+                 ("fmtf32", (5, 5), (2, 3), np.float32, {})]
+        for key, shape, shards, dtype, kw in cases:
+            objects.clear()
+            rs = np.random.RandomState(len(key))
+            X = rs.randn(*shape).astype(dtype)
+            m = matrix.BigMatrix(key, shape=shape, shard_sizes=shards, dtype=dtype, write_header=True, **kw)
+            for bidx in m._block_idxs():
+                sl = tuple(slice(s, e) for s, e in m.__block_idx_to_real_idx__(bidx))
+                blk = X[sl]
+                if key == "fmt3d":
+                    blk = np.squeeze(blk, axis=0)          # autosqueezed put: stored with the full block shape
+                m.put_block(blk, *bidx)
+            out[key] = {"shape": list(shape), "shard_sizes": list(shards), "dtype": np.dtype(dtype).str,
+                        "data": base64.b64encode(X.tobytes()).decode(),
+                        "objects": {k: base64.b64encode(v).decode() for k, v in sorted(objects.items())}}
+    finally:
+        matrix.BigMatrix.put_block_async = patched
+    with open(os.path.join(OUT, "s3_format.json"), "w") as f:
+        json.dump(out, f, indent=0, sort_keys=True)
+    return {k: len(v["objects"]) for k, v in out.items()}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     ref = import_reference()
+    if sys.argv[1:] == ["s3"]:            # only the wire-format fixture
+        print(golden_s3_format(ref))
+        return
     meta = {}
     golden_kernels(ref)
     meta["cholesky_64_8"] = golden_cholesky(ref, 64, 8, 0, "cholesky_64_8")                    # test_cholesky shape
@@ -442,6 +504,7 @@ def main():
     meta["bdfac_16_4_trunc2"] = golden_bdfac(ref, 16, 4, 0, "bdfac_16_4_trunc2", truncate=2)     # test_bdfac_truncated
     meta["bdfac_15_5"] = golden_bdfac(ref, 15, 5, 1, "bdfac_15_5")                               # odd tile count (3)
     meta["structure"] = structure_counts(ref)
+    golden_s3_format(ref)
     with open(os.path.join(OUT, "structure.json"), "w") as f:
         json.dump(meta, f, indent=0, sort_keys=True)
     print("wrote", OUT)

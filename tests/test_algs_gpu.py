@@ -204,7 +204,7 @@ def test_async_upload_and_host_mirror(golden_dir, unique_key, cuda_device):
     A = BigMatrix(unique_key("e2e"), shape=(n, n), shard_sizes=(b, b))
     for (j, k) in A.block_idxs:
         h = torch.from_numpy(np.ascontiguousarray(g["A"][j * b:(j + 1) * b, k * b:(k + 1) * b])).pin_memory()
-        A.put_block(h, j, k)
+        A.put_block(h, j, k, non_blocking=True)
         assert A._ready_event(j, k) is not None
     program, meta = cholesky(A)
     O = meta["outputs"][0]

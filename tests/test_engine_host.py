@@ -304,3 +304,45 @@ def test_several_runner_threads_on_one_program(engine, golden_dir, unique_key):
     assert sum(len(o["executed_messages"]) for o in outs) == len(program.program.nodes)
     assert rel(meta["outputs"][0].numpy(), g["L"]) < 1e-12
     assert program.get_up() == 0
+
+
+@pytest.mark.parametrize("threads", [1, 3])
+def test_eager_program_runs_the_child_post_op_hands_back(engine, golden_dir, unique_key, threads):
+    """LambdaPackProgram(..., eager=True) (reference lambdapack.py:587-592): post_op pops one ready child and returns it
+    as the next operator instead of queueing it; the reference runner executes it next (job_runner.py:113-139).  The
+    engine loop must do the same, otherwise that child is READY for ever and the program stalls in RUNNING."""
+    import concurrent.futures as fs
+    g = np.load(os.path.join(golden_dir, "cholesky_64_8.npz"))
+    A = cpu_matrix(unique_key("eager"), g["A"], 8)
+    program, meta = alg_wrappers.cholesky(A)
+    program.eager = True
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    job_runner.prepare(program)
+    program.start()
+    with fs.ThreadPoolExecutor(threads) as ex:
+        outs = [f.result() for f in [ex.submit(job_runner.lambdapack_run, program, timeout=120) for _ in range(threads)]]
+    assert program.program_status() == lp.PS.SUCCESS
+    assert sum(len(o["executed_messages"]) for o in outs) == len(program.program.nodes)
+    assert rel(meta["outputs"][0].numpy(), g["L"]) < 1e-12
+    assert program.get_up() == 0 and program._runner_active == 0
+
+
+def test_success_is_published_by_the_last_runner_only(engine, golden_dir, unique_key):
+    """A runner that drained the device early must not publish SUCCESS for a peer whose terminator is still being issued:
+    the status flips exactly when the last runner leaves, after that runner's own finish()."""
+    g = np.load(os.path.join(golden_dir, "cholesky_64_8.npz"))
+    A = cpu_matrix(unique_key("last"), g["A"], 8)
+    program, meta = alg_wrappers.cholesky(A)
+    for m in meta["outputs"] + meta["intermediates"]:
+        m.free()
+    job_runner.prepare(program)
+    program.start()
+    with program._lock:
+        program._runner_active += 1          # a second runner is "still issuing"
+    job_runner.lambdapack_run(program, timeout=120)
+    assert program._all_terminators_done and program.program_status() == lp.PS.RUNNING
+    with program._lock:
+        program._runner_active -= 1
+    job_runner.lambdapack_run(program, timeout=120)          # the last runner: nothing left to issue, drains, publishes
+    assert program.program_status() == lp.PS.SUCCESS
