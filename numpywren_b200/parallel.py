@@ -410,215 +410,3 @@ def allreduce_max_int(value: int, device) -> int:
     t = torch.tensor([int(value)], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return int(t.item())
-
-
-# ------------------------------------------------------------------------------------------- bench (N > 1)
-def bench_main(args, metric, unit, workload):
-    """bench.py --gpus N (N>1): each rank generates and factors its block-cyclic share of the same global matrix."""
-    import json
-    import sys
-    import time
-    import torch.distributed as dist
-    from . import _capi, job_runner, kernels
-    from . import lambdapack as lp
-    from .alg_wrappers import cholesky
-    from .matrix import BigMatrix
-
-    grid = init_from_env("nccl")
-    device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
-    _capi.load()
-    n, b = args.n, args.tile
-    nb = n // b
-    X = [torch.empty(b, 128, dtype=torch.float64, device=device) for _ in range(nb)]
-    for j in range(nb):
-        kernels.fill_random(X[j], seed=20261017, row0=j * b)
-
-    def make_input(step):
-        A = BigMatrix(f"bench_A_{step}", shape=(n, n), shard_sizes=(b, b), device=device)
-        for j in range(nb):
-            for k in range(j + 1):
-                if grid.is_mine(A, (j, k)):
-                    t = torch.empty(b, b, dtype=torch.float64, device=device)
-                    kernels._gemm_into(t, None, X[j], X[k], False, True, 1.0, 0.0)
-                    if j == k:
-                        kernels.add_diag(t, float(n))
-                    A._put_block_ref(t, j, k)
-        return A
-
-    plan_s = [0.0]
-
-    def step(i):
-        A = make_input(i)
-        program, meta = cholesky(A)
-        _ = program.program.nodes
-        # static DAG analysis (expansion above; priorities, transfer plan, inbox slots here) is done before the timed
-        # region and reported as config.dag_expand_s / config.plan_s — SURVEY §8d: "DAG pre-expanded"
-        plan_s[0] = job_runner.prepare(program, streams=args.streams, consume_inputs=True)
-        torch.cuda.synchronize()
-        dist.barrier(device_ids=[device.index])
-        l0 = _capi.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        program.start()
-        job_runner.lambdapack_run(program, timeout=3600, streams=args.streams, consume_inputs=True)
-        e1.record()
-        e1.synchronize()
-        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        launches = torch.tensor([_capi.launch_count() - l0], dtype=torch.int64, device=device)
-        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
-        assert program.program_status() == lp.PS.SUCCESS
-        eng = program._engine
-        sent = eng.comm.bytes_sent if eng.comm is not None else 0
-        return float(ms.item()), int(launches.item()), A, program, meta, sent
-
-    def e2e_step(i, host_in, host_out):
-        """Host tiles -> HBM -> factorise -> host tiles on every rank's share, all inside the timed region: the public
-        API with pinned host buffers (BigMatrix.put_block = async H2D, mirror_to_host = write-through D2H)."""
-        torch.cuda.synchronize()
-        dist.barrier(device_ids=[device.index])
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        A = BigMatrix(f"bench_e2e_{i}", shape=(n, n), shard_sizes=(b, b), device=device)
-        for (j, k) in sorted(host_in, key=lambda jk: (jk[1], jk[0])):
-            A.put_block(host_in[(j, k)], j, k, non_blocking=True)
-        program, meta = cholesky(A)
-        O = meta["outputs"][0]
-        O.mirror_to_host(host_out)
-        program.start()
-        job_runner.lambdapack_run(program, timeout=3600, streams=args.streams, consume_inputs=True)
-        O.wait_mirror()
-        e1.record()
-        e1.synchronize()
-        ok = program.program_status() == lp.PS.SUCCESS
-        ms = torch.tensor([e0.elapsed_time(e1) if ok else float("inf")], dtype=torch.float64, device=device)
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        free_all(A, meta)
-        return float(ms.item())
-
-    def residual(meta):
-        """||(L L^T)_jk - A_jk|| / ||A_jk|| on the last diagonal tile, computed by its owner from gathered row tiles."""
-        O = meta["outputs"][0]
-        j = nb - 1
-        owner = grid.owner(O, (j, j))
-        acc = torch.zeros(b, b, dtype=torch.float64, device=device)
-        for i in range(j + 1):
-            src = grid.owner(O, (j, i))
-            t = O._get_block_ref(j, i) if src == grid.rank else torch.empty(b, b, dtype=torch.float64, device=device)
-            dist.broadcast(t, src=src)
-            if grid.rank == owner:
-                kernels._gemm_into(acc, acc, t, t, False, True, 1.0, 1.0)
-        val = torch.zeros(1, dtype=torch.float64, device=device)
-        if grid.rank == owner:
-            ref = torch.empty(b, b, dtype=torch.float64, device=device)
-            kernels._gemm_into(ref, None, X[j], X[j], False, True, 1.0, 0.0)
-            kernels.add_diag(ref, float(n))
-            val[0] = (acc - ref).norm() / ref.norm()
-        dist.broadcast(val, src=owner)
-        return float(val.item())
-
-    def free_all(A, meta):
-        for m in [A] + meta["outputs"] + meta["intermediates"]:
-            m.free()
-
-    resid, sent = None, 0
-    for w in range(args.warmup):
-        ms, _, A, program, meta, sent = step(f"w{w}")
-        if grid.rank == 0:
-            print(f"warmup {w}: {ms:.1f} ms", file=sys.stderr, flush=True)
-        if w == args.warmup - 1:
-            resid = residual(meta)
-        free_all(A, meta)
-        del A, program, meta
-    sampler = None
-    if grid.rank == 0:
-        from bench import ClockSampler  # the driver runs bench.py as __main__ from the repo root
-        sampler = ClockSampler(index=int(os.environ.get("LOCAL_RANK", "0")))
-        sampler.start()
-    times, launches_tot = [], 0
-    for s in range(args.steps):
-        ms, launches, A, program, meta, sent = step(f"s{s}")
-        times.append(ms)
-        launches_tot += launches
-        free_all(A, meta)
-        del A, program, meta
-    clocks = sampler.stop() if sampler is not None else None
-    ms_per_step = float(np.mean(times))
-    value = (n ** 3 / 3.0) / (ms_per_step * 1e-3) * 1e-12
-    sent_t = torch.tensor([sent], dtype=torch.int64, device=device)
-    dist.all_reduce(sent_t, op=dist.ReduceOp.SUM)
-    roofline = None
-    if grid.rank == 0:
-        # dominant kernel alone on rank 0's GPU, against the live-measured fp64 pipe peak (same method as at N=1)
-        import bench as _bench
-        peaks = _bench.measure_peaks(device)
-        wl = _bench.Workload(b, b, device)
-        k_avg, k_min = _bench.measure_dominant_kernel(wl)
-        peak = max(peaks["dmma_pipe_tflops"], peaks["cublas_dgemm_tflops"])
-        ach = 2.0 * b ** 3 / (k_avg * 1e-3) * 1e-12
-        roofline = {"bound": "tensor", "kernel": "gemm_nt_tma_kernel (kernels.syrk, tile update)", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "traffic": _bench.load_traffic(), "flops_per_launch": 2.0 * b ** 3,
-                    "avg_launch_ms": k_avg, "min_launch_ms": k_min,
-                    "peak_source": "measured live on rank 0: max(DMMA issue probe %.2f, cuBLAS DGEMM %.2f) TFLOP/s per GPU" % (
-                        peaks["dmma_pipe_tflops"], peaks["cublas_dgemm_tflops"]),
-                    "whole_job_frac_of_aggregate_peak": value / (peak * grid.world)}
-    # ---- end to end with HOST buffers at this GPU count: every rank stages its own tiles in pinned memory
-    # (written after round 1's GPU budget was spent: opt-in until it has run on hardware once — a failure on one rank
-    # inside a collective step would cost the whole line)
-    e2e = {"value": None, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-           "note": "host-buffer end-to-end is measured at N=1; NPW_B200_BENCH_E2E=1 enables the per-rank staging path here"}
-    if os.environ.get("NPW_B200_BENCH_E2E", "0") != "0":
-        host_in, host_out, ok = {}, {}, 1
-        try:
-            mine = [(j, k) for j in range(nb) for k in range(j + 1) if grid.owner_of_coords(j, k) == grid.rank]
-            if 2 * len(mine) * b * b * 8 > float(os.environ.get("NPW_B200_BENCH_E2E_MAX_GB", "96")) * 2 ** 30:
-                raise MemoryError("pinned staging for this rank's share exceeds NPW_B200_BENCH_E2E_MAX_GB")
-            for (j, k) in mine:
-                t = torch.empty(b, b, dtype=torch.float64, device=device)
-                kernels._gemm_into(t, None, X[j], X[k], False, True, 1.0, 0.0)
-                if j == k:
-                    kernels.add_diag(t, float(n))
-                h = torch.empty(b, b, dtype=torch.float64, pin_memory=True)
-                h.copy_(t)
-                host_in[(j, k)] = h
-                host_out[(j, k)] = torch.empty(b, b, dtype=torch.float64, pin_memory=True)
-                del t
-        except Exception as ex:  # pragma: no cover
-            ok = 0
-            e2e["error"] = repr(ex)
-        # every rank must agree before entering the collective timed steps
-        flag = torch.tensor([ok], dtype=torch.int64, device=device)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 1:
-            e2e_step("w", host_in, host_out)                                           # warm
-            ts = [e2e_step(f"t{r}", host_in, host_out) for r in range(max(1, min(args.steps, 2)))]
-            e_ms = float(np.mean(ts))
-            moved = torch.tensor([len(host_in) * b * b * 8], dtype=torch.int64, device=device)
-            dist.all_reduce(moved, op=dist.ReduceOp.SUM)
-            if np.isfinite(e_ms):
-                e2e = {"value": (n ** 3 / 3.0) / (e_ms * 1e-3) * 1e-12, "unit": unit, "h2d_bytes_per_step": int(moved.item()),
-                       "d2h_bytes_per_step": int(moved.item()), "ms_per_step": e_ms,
-                       "what": "per rank: pinned host lower tiles -> BigMatrix.put_block (async H2D) -> cholesky() -> "
-                               "lambdapack_run -> factor tiles written through to pinned host (D2H) -> wait; max over ranks"}
-        elif "error" not in e2e:
-            e2e["error"] = "another rank could not stage its host buffers"
-        del host_in, host_out
-    if grid.rank == 0:
-        from bench import _dtype_label
-        line = {"metric": metric, "value": value, "unit": unit, "n_gpus": grid.world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": _dtype_label(),
-                "data": "synthetic",
-                "config": {"workload": workload, "process_grid": f"{grid.P}x{grid.Q} block-cyclic over tile index",
-                           "exchange": os.environ.get("NPW_B200_EXCHANGE", "symm"),
-                           "tile_tasks": nb * (nb + 1) * (nb + 2) // 6, "streams": args.streams,
-                           "l2": "inputs larger than L2; every step regenerates its input",
-                           "nvlink_bytes_per_step": int(sent_t.item()), "residual_LLt_minus_A": resid,
-                           "plan_s": plan_s[0],
-                           "algorithmic_flops_per_step": n ** 3 / 3.0},
-                "roofline": roofline, "cpu_baseline": None,
-                "e2e": e2e,
-                "gpu_launches": launches_tot, "clocks": clocks}
-        print(json.dumps(line), flush=True)
-    dist.barrier(device_ids=[device.index])
-    dist.destroy_process_group()
-    return 0

@@ -237,18 +237,51 @@ def test_experimental_i8emu_mode_through_the_engine(engine, unique_key, monkeypa
     assert len(program._engine._digits) == 0                      # every digit cache entry was released
 
 
+def _host_bench_ctx(bench):
+    """bench.Ctx without a GPU / process group: one rank, tiles on the host device."""
+    ctx = object.__new__(bench.Ctx)
+    ctx.world, ctx.rank, ctx.local_rank, ctx.device, ctx.grid = 1, 0, 0, torch.device("cpu"), None
+    return ctx
+
+
 def test_bench_gpu_step_flow_on_the_host(engine, monkeypatch):
-    """bench.py's timed step (resident input -> cholesky() -> prepare -> start -> lambdapack_run) with the host harness:
-    the flow the driver runs at round end, minus the device."""
+    """bench.py's timed step (resident input -> cholesky() -> prepare -> start -> lambdapack_run), its residual check and
+    its whole-program parity check against the oracle, with the host harness: the flow the driver runs at round end,
+    minus the device."""
     import bench
     monkeypatch.setattr(bench.torch.cuda, "synchronize", lambda device=None: None)
-    wl = bench.Workload(512, 128, torch.device("cpu"))
-    ms, launches, A, program, meta = bench.gpu_step(wl, streams=4)
+    ctx = _host_bench_ctx(bench)
+    wl = bench.CholeskyWorkload(ctx, 512, 128)
+    ms, launches, plan_s, A, program, meta = bench.cholesky_step(ctx, wl, streams=4)
     assert program.program_status() == lp.PS.SUCCESS and launches > 0
     assert getattr(program, "_engine", None) is not None and program._engine.n_streams == 4
-    resid = bench.residual_check(wl, meta["outputs"][0], [(0, 0), (3, 0), (3, 3), (2, 1)])
-    assert resid < 1e-13
-    bench.free_all(A, meta)
+    assert bench.residual_check(ctx, wl, meta["outputs"][0]) < 1e-13
+    bench.free_all(A, *meta["outputs"], *meta["intermediates"])
+    t, L, tiles, cores = bench.cpu_cholesky_sample(512, 128)
+    par = bench.parity_vs_oracle(ctx, 512, 128, 4, L, tiles)
+    assert par["ok"] and par["rel_fro"] < 1e-13 and par["tiles_compared"] == 10
+    L[(3, 1)] = L[(3, 1)] + 1e-6                      # the check must be able to fail
+    assert not bench.parity_vs_oracle(ctx, 512, 128, 4, L, tiles)["ok"]
+    tr = bench.utilisation_trace(ctx, wl, 4, slices=4)
+    assert len(tr["busy_fraction_per_rank"]) == 1 and set(tr["rank0_kernel_ms"]) == {"chol", "trsm", "syrk"}
+
+
+def test_bench_reference_arm_composes_the_same_workload(capsys, monkeypatch):
+    """--impl reference: same config/metric as the GPU arm, step time composed from the oracle's kernel times by the
+    task counts of the workload, all host cores even under torchrun's OMP_NUM_THREADS=1."""
+    import json
+    import bench
+    monkeypatch.setenv("OMP_NUM_THREADS", "1")
+    args = type("A", (), dict(workload="cholesky", n=1024, tile=128, gpus=2, steps=2, warmup=1, cpu_n=512, cols=512))()
+    assert bench.run_reference_arm(args) == 0
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == bench.METRIC and line["config"]["workload"] == bench.workload_name(args)
+    ks = line["config"]["kernel_seconds"]
+    c, r, s = bench.chol_task_counts(8)
+    assert (c, r, s) == (8, 28, 84)
+    assert abs(line["ms_per_step"] - 1e3 * (c * ks["chol"] + r * ks["trsm"] + s * ks["syrk"])) < 1e-6 * line["ms_per_step"]
+    assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1) and line["e2e"]["value"] == line["value"]
+    assert line["config"]["cross_check"]["measured_end_to_end_s"] > 0
 
 
 def test_duplicate_and_premature_messages_are_harmless(engine, golden_dir, unique_key):
