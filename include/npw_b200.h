@@ -84,10 +84,10 @@ int npw_gemm_f64(double* C, int64_t ldc,
  * scipy.linalg.blas.dtrsm(1.0, x.T, y, lower=0, side=1) = y * x^{-T}
  *                                                   (kernels.py:254-257)
  *   B_out[m,n] = B[m,n] * L[n,n]^{-T},  L lower-triangular (strict upper
- *   ignored).  B_out may alias B.  `work` must hold npw_trsm_work_bytes(m,n)
- *   bytes of device scratch.  If `invdiag` is non-NULL it must be the buffer
- *   npw_potrf_l_f64 / npw_trtri_diag_f64 produced for this L (saves the
- *   diagonal-block inversion).
+ *   ignored).  B_out may alias B (the solve works in place in B_out).
+ *   `invdiag` and `work` are accepted for ABI stability and ignored: the
+ *   128-column leaves substitute against the diagonal blocks of L directly
+ *   (npw_trsm_work_bytes returns a token size).
  * ---------------------------------------------------------------------- */
 size_t npw_trsm_work_bytes(int64_t m, int64_t n);
 int npw_trsm_rlt_f64(double* B_out, int64_t ldbo,

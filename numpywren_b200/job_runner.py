@@ -321,9 +321,9 @@ class TileEngine:
             elif fn is kernels.chol and len(args) == 1:
                 out = args[0] if can_overwrite(0) else None
                 consumed = 0 if out is not None else None
-                L, info, inv = kernels.chol_async(args[0], want_inverse=True, out=out)
+                # trsm substitutes against the diagonal blocks of L itself (panel_kernel): no inverses to hand over
+                L, info, _ = kernels.chol_async(args[0], want_inverse=False, out=out)
                 self.infos.append((node, info))
-                self.invdiag[_tile_key(*node.writes[0])] = inv
                 results = L
             else:
                 results = fn(*args, **(node.call.kwargs or {}))

@@ -40,7 +40,7 @@ def test_identity_and_sizes():
     assert lib.npw_invdiag_bytes(4096) == 32 * 128 * 128 * 8
     assert lib.npw_invdiag_bytes(130) == 2 * 128 * 128 * 8
     assert lib.npw_potrf_work_bytes(4096) == 4096 * 128 * 8 + 32 * 128 * 128 * 8
-    assert lib.npw_trsm_work_bytes(4096, 4096) == 4096 * 128 * 8 + 32 * 128 * 128 * 8
+    assert lib.npw_trsm_work_bytes(4096, 4096) == 16          # the solve works in place: the argument is kept for ABI stability
     assert lib.npw_trsm_work_bytes(0, 10) == 0
 
 
@@ -52,7 +52,7 @@ def test_argument_validation_happens_before_cuda():
     assert lib.npw_syrk_f64(p, 2, p, 4, p, 4, p, 4, 4, 4, 4, None) == -2     # ldc < n
     assert lib.npw_syrk_f64(p, 4, p, 4, p, 4, p, 4, 4, 4, -1, None) == -11
     assert lib.npw_gemm_f64(p, 4, 0, 0, p, 2, 0, p, 4, 0, 4, 4, 4, 1.0, 0.0, None) == -6   # lda < k
-    assert lib.npw_trsm_rlt_f64(p, 4, p, 4, p, 4, 4, 4, None, None, None) == -10            # no workspace
+    assert lib.npw_trsm_rlt_f64(p, 4, p, 2, p, 4, 4, 4, None, None, None) == -4             # ldl < n
     assert lib.npw_potrf_l_f64(p, 4, p, 4, 4, None, None, None, None) == -6                  # no info pointer
     assert lib.npw_addn_f64(p, None, 1, 4, None) == -2
     arr = (ctypes.c_void_p * 1)(p)

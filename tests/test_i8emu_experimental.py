@@ -64,5 +64,6 @@ def test_syrk_i8emu_in_place_and_lower_only(cuda_device):
     exact = s - x @ x.T
     i, j = np.indices(c.shape)
     low = j // 64 * 64 <= i // 128 * 128 + 127              # 128 x 64 tiles touching the lower triangle are computed
-    assert np.abs(c[low] - exact[low]).max() < 1e-9
+    # 6 digits: 4.7e-12 of |x_i||y_j| per entry (profiles/r02b_syrk_i8emu_timing.jsonl), |x_i|^2 ~ k = 256
+    assert np.abs(c[low] - exact[low]).max() < 1e-10 * 256
     assert np.array_equal(c[~low], s[~low])                  # the others are left alone

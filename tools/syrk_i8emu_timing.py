@@ -12,8 +12,10 @@ sys.path.insert(0, ROOT)
 from numpywren_b200 import kernels  # noqa: E402
 
 
-def timed(fn, reps=5):
-    fn(); torch.cuda.synchronize()
+def timed(fn, reps=20, warm=5):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
     for _ in range(reps):
