@@ -3,19 +3,23 @@
 // Q = I - V T V^T.  Same Householder convention as LAPACK dlarfg/dlarft, so V, T, R match the reference up to rounding.
 //
 // Blocked right-looking algorithm, panel width 32:
-//   panel   : ONE cooperative kernel factors the (m-j0) x 32 panel.  Rows are split over the CTAs of the grid; a warp
-//             reads a whole panel row as one coalesced 256-byte request (lane = column).  Per column there is a single
+//   panel   : ONE kernel (co-resident grid, <= 1 CTA per SM) factors the (m-j0) x 32 panel.  Rows are split over the
+//             CTAs; each CTA keeps its row chunk in shared memory for all 32 column steps.  Per column there is a single
 //             pass over the rows that (i) applies reflector j, (ii) accumulates the dot products column j+1 needs
 //             (norm + w = P^T x) and (iii) the Gram entries V[:,0:j]^T v_j that dlarft needs, all in one 32-lane
-//             vector, followed by ONE grid-wide reduction (grid.sync) per column.
-//   update  : Wt = C^T V_p (split-K "TN" kernel: k = rows, deterministic two-phase reduction), Wt := Wt T_p,
-//             C -= V_p Wt^T through the DMMA GEMM core (NT, k = 32).
-//   T       : Gram matrix G = V^T V (same split-K kernel), then T[0:j0, panel] = -T[0:j0,0:j0] G[0:j0,panel] T_pp.
-#include <cooperative_groups.h>
+//             vector, followed by ONE all-gather of the per-CTA vectors.  The all-gather is flag-in-data: every double
+//             travels as two 64-bit packets {32 payload bits | 32-bit sequence number}; readers poll the packets
+//             themselves, so a column step costs one L2 store->load latency instead of a grid barrier plus a reduction
+//             (round 1: 14 us per column, cooperative grid.sync; now one hop).  Every CTA adds the vectors in the same
+//             fixed order, so all CTAs derive bit-identical Householder scalars and the result is deterministic.
+//   update  : Wt = C^T V_p  split-K "TN" product on the fp64 tensor pipe (DMMA, k = rows), reduced in a fixed order
+//             and multiplied by T_p in the same kernel;  C -= V_p (Wt T_p)^T  by a streaming rank-32 DMMA kernel
+//             (HBM-bound: 2 x 32 flop per element read and written).
+//   T       : Gram matrix G = V^T V (same TN kernel, upper tiles only), then per panel
+//             T[0:j0, panel] = -T[0:j0,0:j0] G[0:j0,panel] T_pp  (one small kernel per panel).
+#include <stdlib.h>
 
 #include "npw_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace npw {
 
@@ -29,9 +33,16 @@ int launch_fill2d(double* A, int64_t lda, int64_t rows, int64_t cols, int mode, 
 namespace {
 
 constexpr int QW = 32;            // panel width
-constexpr int QTHREADS = 256;     // 8 warps
+constexpr int QTHREADS = 512;     // 16 warps
 constexpr int QWARPS = QTHREADS / 32;
-constexpr int MAX_GRID = 256;
+constexpr int MAX_GRID = 160;     // upper bound on the CTAs of a panel launch (<= SM count)
+constexpr int QMAXQ = (MAX_GRID + QWARPS - 1) / QWARPS;   // vectors one reader group adds per step
+
+// packet scratch, per step parity: [MAX_GRID][32 doubles x 2 packets] partial vectors, then [32 x 2] the pivot row
+constexpr int PK_PER_VEC = 2 * QW;
+constexpr int PK_STRIDE = (MAX_GRID + 1) * PK_PER_VEC;
+constexpr size_t PK_BYTES = 2 * static_cast<size_t>(PK_STRIDE) * sizeof(uint64_t);
+constexpr long long QR_SPIN_LIMIT = 4000000000ll;          // ~2 s of polling: give up (sets *err) instead of hanging
 
 struct PanelArgs {
   double* V;       // m x n working matrix (row-major, ldv); panel columns [j0, j0+w)
@@ -42,20 +53,37 @@ struct PanelArgs {
   double* T;       // n x n output, ldt (only the w x w diagonal block of this panel is written)
   int64_t ldt;
   double* tau;     // n
-  double* scratch; // 2 x MAX_GRID x 64 doubles: per-CTA partial vectors (double-buffered) + pivot rows
+  uint64_t* packets;   // PK_BYTES, zeroed once per factorisation
+  uint32_t seq0;       // first sequence number of this launch (unique within the factorisation, never 0)
+  int* err;            // set to 1 if a poll timed out
 };
 
-// scratch layout per parity buffer: [cta][32] partial sums, then [32] pivot row, starting at parity * SCR_STRIDE
-constexpr int SCR_STRIDE = MAX_GRID * QW + QW;
+// A double as two self-validating 64-bit packets (each 8-byte access is single-copy atomic, so no fence or separate
+// flag is needed: a packet is either the old one or the complete new one).
+__device__ __forceinline__ void ll_store(uint64_t* slot, double v, uint32_t seq) {
+  const uint64_t bits = static_cast<uint64_t>(__double_as_longlong(v));
+  const uint64_t tag = static_cast<uint64_t>(seq) << 32;
+  const uint64_t w0 = (bits & 0xffffffffull) | tag;
+  const uint64_t w1 = (bits >> 32) | tag;
+  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void ll_load(const uint64_t* slot, uint64_t& w0, uint64_t& w1) {
+  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+}
+__device__ __forceinline__ bool ll_valid(uint64_t w0, uint64_t w1, uint32_t seq) {
+  return static_cast<uint32_t>(w0 >> 32) == seq && static_cast<uint32_t>(w1 >> 32) == seq;
+}
+__device__ __forceinline__ double ll_value(uint64_t w0, uint64_t w1) {
+  return __longlong_as_double(static_cast<long long>((w0 & 0xffffffffull) | (w1 << 32)));
+}
 
 // SMEM = true: the CTA's row chunk of the panel (<= QR_SMEM_ROWS rows x 32 columns) is loaded into shared memory once,
 // all 32 column passes run there, and the chunk is written back once (2 global passes instead of 64).
-constexpr int QR_SMEM_ROWS = 768;                    // 768 x 32 x 8 B = 192 KB
+constexpr int QR_SMEM_ROWS = 672;                    // 672 x 32 x 8 B = 168 KB (+ ~25 KB static)
 
 template <bool SMEM>
-__global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
+__global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(PanelArgs p) {
   extern __shared__ __align__(16) double s_chunk[];
-  cg::grid_group grid = cg::this_grid();
   const int G = gridDim.x;
   const int cta = blockIdx.x;
   const int lane = threadIdx.x & 31;
@@ -68,12 +96,11 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
   const bool lane_ok = lane < w;
   double* Vp = p.V + p.j0;                           // column offset of the panel
 
-  __shared__ double s_part[QWARPS][QW];
-  __shared__ double s_vec[QW];                       // reduced vector g
-  __shared__ double s_prow[QW];
+  __shared__ double s_part[QWARPS][QW];              // per-warp partial vectors of a pass
+  __shared__ double s_red[QWARPS][QW];               // per-reader-group sums of the gathered vectors
   __shared__ double s_T[QW][QW + 1];
+  __shared__ double s_Z[QW][QW];                     // Gram vectors z_j = V[:,0:j]^T v_j (CTA 0 builds T from them)
   __shared__ double s_tau[QW];
-  __shared__ double s_sc[4];                         // tau_j, scale_j, beta_j
 
   for (int e = threadIdx.x; e < QW * (QW + 1); e += QTHREADS) (&s_T[0][0])[e] = 0.0;
 
@@ -86,6 +113,59 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
     __syncthreads();
   }
 
+  // publish this CTA's vector for step `step` (warp 0) and, if it owns row `prow`, that row of the panel (warp 2)
+  auto publish = [&](int step, int prow) {
+    uint64_t* base = p.packets + static_cast<size_t>(step & 1) * PK_STRIDE;
+    const uint32_t seq = p.seq0 + static_cast<uint32_t>(step);
+    if (warp == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < QWARPS; ++q) s += s_part[q][lane];
+      ll_store(base + static_cast<size_t>(cta) * PK_PER_VEC + 2 * lane, s, seq);
+    } else if (warp == 2 && prow >= r_lo && prow < r_hi) {
+      ll_store(base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane, lane_ok ? rowptr(prow)[lane] : 0.0, seq);
+    }
+  };
+  // all-gather + reduction of step `step`: returns g[lane] (sum over all CTAs, fixed order) and the pivot row entry
+  auto gather = [&](int step, bool need_pivot, double& g_l, double& prow_l) {
+    const uint64_t* base = p.packets + static_cast<size_t>(step & 1) * PK_STRIDE;
+    const uint32_t seq = p.seq0 + static_cast<uint32_t>(step);
+    uint64_t a0[QMAXQ], a1[QMAXQ], b0 = 0, b1 = 0;
+    const long long t0 = clock64();
+    bool ok = *static_cast<volatile int*>(p.err) != 0;     // a poll that timed out earlier: do not wait again
+    while (!ok) {
+#pragma unroll
+      for (int u = 0; u < QMAXQ; ++u) {
+        const int q = warp + u * QWARPS;
+        if (q < G) ll_load(base + static_cast<size_t>(q) * PK_PER_VEC + 2 * lane, a0[u], a1[u]);
+      }
+      if (need_pivot) ll_load(base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane, b0, b1);
+      ok = !need_pivot || ll_valid(b0, b1, seq);
+#pragma unroll
+      for (int u = 0; u < QMAXQ; ++u) {
+        const int q = warp + u * QWARPS;
+        if (q < G) ok = ok && ll_valid(a0[u], a1[u], seq);
+      }
+      if (!ok && clock64() - t0 > QR_SPIN_LIMIT) {
+        *static_cast<volatile int*>(p.err) = 1;
+        break;
+      }
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int u = 0; u < QMAXQ; ++u) {
+      const int q = warp + u * QWARPS;
+      if (q < G) s += ll_value(a0[u], a1[u]);
+    }
+    s_red[warp][lane] = s;
+    prow_l = need_pivot ? ll_value(b0, b1) : 0.0;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < QWARPS; ++q) t += s_red[q][lane];
+    g_l = t;
+  };
+
   // ---- initial partials for column 0: g[c] = sum_{r > j0} x_r * P[r][c], x = column 0
   {
     double acc = 0.0;
@@ -97,65 +177,29 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
     }
     s_part[warp][lane] = acc;
     __syncthreads();
-    if (warp == 0) {
-      double s = 0.0;
-      for (int q = 0; q < QWARPS; ++q) s += s_part[q][lane];
-      p.scratch[cta * QW + lane] = s;
-      if (p.j0 >= r_lo && p.j0 < r_hi)
-        p.scratch[MAX_GRID * QW + lane] = lane_ok ? rowptr(p.j0)[lane] : 0.0;
-    }
+    publish(0, p.j0);
   }
 
   for (int j = 0; j < w; ++j) {
     const int gj = p.j0 + j;                         // pivot row / column (global)
-    const int par = j & 1;
-    __threadfence();
-    grid.sync();
-    // ---- reduce the partial vectors of all CTAs (every CTA redundantly)
-    const double* scr = p.scratch + par * SCR_STRIDE;
-    {
-      double s = 0.0;
-      {
-        // all partial vectors are fetched with independent loads (fixed order of addition: deterministic result)
-        double v[4];
-        int q = warp;
-        for (; q + 3 * QWARPS < G; q += 4 * QWARPS) {
-#pragma unroll
-          for (int u = 0; u < 4; ++u) v[u] = __ldcg(scr + (q + u * QWARPS) * QW + lane);
-          s += v[0]; s += v[1]; s += v[2]; s += v[3];
-        }
-        for (; q < G; q += QWARPS) s += __ldcg(scr + q * QW + lane);
-      }
-      s_part[warp][lane] = s;
-      __syncthreads();
-      if (warp == 0) {
-        double t = 0.0;
-        for (int q = 0; q < QWARPS; ++q) t += s_part[q][lane];
-        s_vec[lane] = t;
-        s_prow[lane] = __ldcg(scr + MAX_GRID * QW + lane);
-      }
-      __syncthreads();
+    double g_l, prow_l;
+    gather(j, true, g_l, prow_l);
+    // lanes c >= j of g: dot products for column j (c == j: squared norm below the pivot);
+    // lanes i < j-1: Gram entries of column j-1 (kept for T)
+    if (j > 0 && cta == 0 && warp == 1) s_Z[j - 1][lane] = g_l;
+    // ---- Householder scalars (dlarfg), redundantly in every thread (identical inputs -> identical results)
+    const double alpha = __shfl_sync(0xffffffffu, prow_l, j);
+    const double xn2 = __shfl_sync(0xffffffffu, g_l, j);
+    double tau = 0.0, scale = 0.0, beta = alpha;
+    if (xn2 > 0.0) {
+      const double nrm = sqrt(alpha * alpha + xn2);
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      tau = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
     }
-    // lanes c >= j of s_vec: dot products for column j (c == j: squared norm below the pivot)
-    // lanes c <  j-1 ... of the PREVIOUS column's Gram are folded in below (see z handling)
-    // ---- Householder scalars (dlarfg)
-    if (threadIdx.x == 0) {
-      const double alpha = s_prow[j];
-      const double xn2 = s_vec[j];
-      double tau = 0.0, scale = 0.0, beta = alpha;
-      if (xn2 > 0.0) {
-        const double nrm = sqrt(alpha * alpha + xn2);
-        beta = alpha >= 0.0 ? -nrm : nrm;
-        tau = (beta - alpha) / beta;
-        scale = 1.0 / (alpha - beta);
-      }
-      s_sc[0] = tau; s_sc[1] = scale; s_sc[2] = beta;
-      s_tau[j] = tau;
-    }
-    __syncthreads();
-    const double tau = s_sc[0], scale = s_sc[1], beta = s_sc[2];
+    if (threadIdx.x == 0) s_tau[j] = tau;
     // w_c = v^T P[:, c] = prow[c] + scale * g[c]   (c > j)
-    const double wc = (lane > j && lane_ok) ? s_prow[lane] + scale * s_vec[lane] : 0.0;
+    const double wc = (lane > j && lane_ok) ? prow_l + scale * g_l : 0.0;
     const double tw = tau * wc;
 
     // ---- one pass over this CTA's rows: apply reflector j, store v_j, accumulate for column j+1 and the Gram of v_j
@@ -182,82 +226,157 @@ __global__ void __launch_bounds__(QTHREADS) qr_panel_kernel(PanelArgs p) {
       if (lane == j) v = vr;
       if (lane_ok && lane >= j) rowp[lane] = v;
       if (lane < j) acc = fma(v, vr, acc);            // V[r][i] * v_j[r]
-      if (j + 1 < w && r > gj + 1) {
-        const double xn = __shfl_sync(0xffffffffu, v, j + 1);
-        if (lane > j) acc = fma(xn, v, acc);
-      } else if (j + 1 < w) {
-        __shfl_sync(0xffffffffu, v, j + 1);           // keep the warp converged on the shuffle
-      }
+      const double xn = __shfl_sync(0xffffffffu, v, (j + 1) & 31);
+      if (j + 1 < w && r > gj + 1 && lane > j) acc = fma(xn, v, acc);
     }
     s_part[warp][lane] = acc;
     __syncthreads();
-    if (warp == 0) {
-      double s = 0.0;
-      for (int q = 0; q < QWARPS; ++q) s += s_part[q][lane];
-      double* out = p.scratch + (par ^ 1) * SCR_STRIDE;
-      out[cta * QW + lane] = s;
-      const int gn = gj + 1;                          // next pivot row
-      if (j + 1 < w && gn >= r_lo && gn < r_hi && gn < p.m)
-        out[MAX_GRID * QW + lane] = lane_ok ? rowptr(gn)[lane] : 0.0;
-    }
-    // ---- the Gram vector z_i = V[:,i]^T v_{j-1} (i < j-1) reduced this round belongs to column j-1 of T
-    if (j > 0 && cta == 0 && threadIdx.x == 0) {
-      const int jj = j - 1;
-      const double tj = s_tau[jj];
-      for (int i = 0; i < jj; ++i) {
-        double t = 0.0;
-        for (int q = i; q < jj; ++q) t += s_T[i][q] * s_vec[q];   // T[0:jj,0:jj] upper-triangular times z
-        s_T[i][jj] = -tj * t;
-      }
-      s_T[jj][jj] = tj;
-    }
-    __syncthreads();
+    publish(j + 1, (j + 1 < w && gj + 1 < p.m) ? gj + 1 : -1);
   }
-  // ---- last column's Gram vector
-  __threadfence();
-  grid.sync();
+  // ---- last column's Gram vector, then T of this panel (dlarft, forward columnwise) by one warp of CTA 0
   {
-    const double* scr = p.scratch + (w & 1) * SCR_STRIDE;
-    double s = 0.0;
-    for (int q = warp; q < G; q += QWARPS) s += __ldcg(scr + q * QW + lane);
-    s_part[warp][lane] = s;
-    __syncthreads();
-    if (warp == 0) {
-      double t = 0.0;
-      for (int q = 0; q < QWARPS; ++q) t += s_part[q][lane];
-      s_vec[lane] = t;
+    double g_l, prow_l;
+    gather(w, false, g_l, prow_l);
+    if (cta == 0 && warp == 1) {
+      s_Z[w - 1][lane] = g_l;
+      __syncwarp();
+      for (int jj = 0; jj < w; ++jj) {
+        const double tj = s_tau[jj];
+        double t = 0.0;
+        if (lane < jj)
+          for (int q = lane; q < jj; ++q) t = fma(s_T[lane][q], s_Z[jj][q], t);   // T[0:jj,0:jj] (upper) times z_jj
+        if (lane < jj) s_T[lane][jj] = -tj * t;
+        if (lane == jj) s_T[jj][jj] = tj;
+        __syncwarp();
+      }
     }
     __syncthreads();
   }
   if (cta == 0) {
-    if (threadIdx.x == 0) {
-      const int jj = w - 1;
-      const double tj = s_tau[jj];
-      for (int i = 0; i < jj; ++i) {
-        double t = 0.0;
-        for (int q = i; q < jj; ++q) t += s_T[i][q] * s_vec[q];
-        s_T[i][jj] = -tj * t;
-      }
-      s_T[jj][jj] = tj;
-    }
-    __syncthreads();
     for (int e = threadIdx.x; e < w * w; e += QTHREADS) {
       const int i = e / w, c = e - i * w;
       p.T[static_cast<int64_t>(p.j0 + i) * p.ldt + p.j0 + c] = (c >= i) ? s_T[i][c] : 0.0;
     }
     for (int e = threadIdx.x; e < w; e += QTHREADS) p.tau[p.j0 + e] = s_tau[e];
+    // a timed-out poll means the factorisation is garbage: make that impossible to miss
+    if (threadIdx.x == 0 && *static_cast<volatile int*>(p.err) != 0)
+      p.T[static_cast<int64_t>(p.j0) * p.ldt + p.j0] = __longlong_as_double(0x7ff8000000000000ll);
   }
   if (SMEM) {                                        // write the factored chunk back (V below the diagonal, explicit unit/zeros)
-    __syncthreads();
     for (int r = r_lo + warp; r < r_hi; r += QWARPS)
       if (lane_ok) Vp[static_cast<int64_t>(r) * p.ldv + lane] = s_chunk[static_cast<size_t>(r - r_lo) * QW + lane];
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Split-K "TN" product for tall operands: P[s] = A[ks:ke, 0:M]^T * B[ks:ke, 0:N], 64x64 output tiles.
+// Split-K "TN" product for tall operands: P[s] = A[ks:ke, 0:M]^T * B[ks:ke, 0:N].
 // A is rows x M (lda), B is rows x N (ldb); the reduction dimension is the (long) row index.
+//
+// tn_dmma_kernel (the fast path): 64 x 32 output tile per CTA on the fp64 tensor pipe.  A 32-row chunk of both operands
+// is staged in shared memory as it lies in memory (row = k index, padded to 68 / 36 doubles so that the m8n8k4 fragment
+// loads — lane (g, c) reads element [4 ks + c][8 i + g] — touch 16 different banks per half warp); the next chunk is
+// prefetched into registers while the current one feeds the DMMAs.  8 warps, warp tile 16 x 16 (2 x 2 DMMA tiles).
+// tn_partial_kernel (generic): plain DFMA, any alignment.
 // ------------------------------------------------------------------------------------------------
+constexpr int TDM = 64, TDN = 32, TDK = 32;
+constexpr int TD_LDA = TDM + 4, TD_LDB = TDN + 4;
+constexpr int TD_SMEM = 2 * TDK * (TD_LDA + TD_LDB) * static_cast<int>(sizeof(double));   // 53248 B
+
+__global__ void __launch_bounds__(256, 3) tn_dmma_kernel(double* __restrict__ P, const double* __restrict__ A, int64_t lda,
+                                                         const double* __restrict__ B, int64_t ldb, int rows, int M, int N,
+                                                         int kchunk, int upper_only) {
+  extern __shared__ __align__(16) double td_smem[];
+  const int tm = blockIdx.y * TDM, tn = blockIdx.x * TDN, sp = blockIdx.z;
+  if (upper_only && tn + TDN - 1 < tm) return;              // tile entirely below the diagonal: never read
+  double* As = td_smem;                                     // [2][TDK][TD_LDA]
+  double* Bs = td_smem + 2 * TDK * TD_LDA;                  // [2][TDK][TD_LDB]
+  const int k0 = sp * kchunk, k1 = min(rows, k0 + kchunk);
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;                  // warp tile: rows 16 wm.., cols 16 wn..
+  // staging assignment: A chunk = 32 rows x 32 double2 -> 4 per thread; B chunk = 32 rows x 16 double2 -> 2 per thread
+  double2 ra[4], rb[2];
+  auto fetch = [&](int kb) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = t + 256 * u;
+      const int r = kb + (e >> 5), col = tm + 2 * (e & 31);
+      double2 v = make_double2(0.0, 0.0);
+      if (r < k1) {
+        const double* src = A + static_cast<int64_t>(r) * lda + col;
+        if (col + 1 < M) v = *reinterpret_cast<const double2*>(src);
+        else if (col < M) v.x = src[0];
+      }
+      ra[u] = v;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = t + 256 * u;
+      const int r = kb + (e >> 4), col = tn + 2 * (e & 15);
+      double2 v = make_double2(0.0, 0.0);
+      if (r < k1) {
+        const double* src = B + static_cast<int64_t>(r) * ldb + col;
+        if (col + 1 < N) v = *reinterpret_cast<const double2*>(src);
+        else if (col < N) v.x = src[0];
+      }
+      rb[u] = v;
+    }
+  };
+  auto stage = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = t + 256 * u;
+      *reinterpret_cast<double2*>(As + (buf * TDK + (e >> 5)) * TD_LDA + 2 * (e & 31)) = ra[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int e = t + 256 * u;
+      *reinterpret_cast<double2*>(Bs + (buf * TDK + (e >> 4)) * TD_LDB + 2 * (e & 15)) = rb[u];
+    }
+  };
+  double acc[2][2][2] = {};
+  int buf = 0;
+  if (k0 < k1) {
+    fetch(k0);
+    stage(0);
+  }
+  __syncthreads();
+  for (int kb = k0; kb < k1; kb += TDK) {
+    const bool more = kb + TDK < k1;
+    if (more) fetch(kb + TDK);                              // global loads in flight while this chunk is multiplied
+    const double* Ab = As + buf * TDK * TD_LDA + 16 * wm + g;
+    const double* Bb = Bs + buf * TDK * TD_LDB + 16 * wn + g;
+#pragma unroll
+    for (int ks = 0; ks < TDK / 4; ++ks) {
+      double a[2], b[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) a[i] = Ab[(4 * ks + c) * TD_LDA + 8 * i];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = Bb[(4 * ks + c) * TD_LDB + 8 * j];
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (more) stage(buf ^ 1);                               // the other buffer was last read before the previous barrier
+    __syncthreads();
+    buf ^= 1;
+  }
+  double* Ps = P + static_cast<int64_t>(sp) * M * N;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int r = tm + 16 * wm + 8 * i + g;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int col = tn + 16 * wn + 8 * j + 2 * c;
+      if (col < N) Ps[static_cast<int64_t>(r) * N + col] = acc[i][j][0];
+      if (col + 1 < N) Ps[static_cast<int64_t>(r) * N + col + 1] = acc[i][j][1];
+    }
+  }
+}
+
 constexpr int TT = 64, TKC = 16;
 
 __global__ void __launch_bounds__(256) tn_partial_kernel(double* __restrict__ P, const double* __restrict__ A, int64_t lda,
@@ -304,20 +423,62 @@ __global__ void __launch_bounds__(256) tn_partial_kernel(double* __restrict__ P,
   }
 }
 
+// C (M x N, ldc) = sum of the nsplit partial products, added in a fixed order (deterministic).  With Tm != nullptr
+// (N <= 32) the sum is multiplied from the right by the N x N matrix Tm (ldt) before it is stored:
+// C = (sum_s P[s]) Tm — the "Wt T_p" of the compact-WY update, fused here because Wt is never needed by itself.
 __global__ void __launch_bounds__(256) tn_reduce_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ P,
-                                                        int M, int N, int nsplit) {
+                                                        int M, int N, int nsplit, const double* __restrict__ Tm, int64_t ldt) {
   const int64_t total = static_cast<int64_t>(M) * N;
-  for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
-       e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  if (Tm == nullptr) {
+    for (int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
+         e += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+      double s = 0.0;
+      for (int q = 0; q < nsplit; ++q) s += P[static_cast<int64_t>(q) * total + e];
+      const int64_t r = e / N, c = e - r * N;
+      C[r * ldc + c] = s;
+    }
+    return;
+  }
+  __shared__ double sT[QW][QW + 1];
+  __shared__ double sW[8][QW + 1];
+  for (int e = threadIdx.x; e < QW * QW; e += 256) {
+    const int i = e / QW, c = e % QW;
+    sT[i][c] = (i < N && c < N) ? Tm[static_cast<int64_t>(i) * ldt + c] : 0.0;
+  }
+  const int rr = threadIdx.x >> 5, c = threadIdx.x & 31;
+  for (int r0 = blockIdx.x * 8; r0 < M; r0 += gridDim.x * 8) {
+    const int r = r0 + rr;
     double s = 0.0;
-    for (int q = 0; q < nsplit; ++q) s += P[static_cast<int64_t>(q) * total + e];   // fixed order: deterministic
-    const int64_t r = e / N, c = e - r * N;
-    C[r * ldc + c] = s;
+    if (r < M && c < N) {
+      const int64_t e = static_cast<int64_t>(r) * N + c;
+      for (int q = 0; q < nsplit; ++q) s += P[static_cast<int64_t>(q) * total + e];
+    }
+    __syncthreads();                                         // sT ready (first trip) / sW free again
+    sW[rr][c] = s;
+    __syncthreads();
+    if (r < M && c < N) {
+      double o = 0.0;
+#pragma unroll 8
+      for (int q = 0; q < QW; ++q) o = fma(sW[rr][q], sT[q][c], o);
+      C[static_cast<int64_t>(r) * ldc + c] = o;
+    }
   }
 }
 
-inline int tn_nsplit(int64_t rows, int64_t M, int64_t N) {
-  const int64_t tiles = ((M + TT - 1) / TT) * ((N + TT - 1) / TT);
+inline bool aligned16(const void* p, int64_t ld) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0 && (ld % 2 == 0); }
+
+inline int64_t tn_tiles(int64_t M, int64_t N, int upper_only) {
+  const int64_t gm = (M + TDM - 1) / TDM, gn = (N + TDN - 1) / TDN;
+  if (!upper_only) return gm * gn;
+  int64_t cnt = 0;
+  for (int64_t i = 0; i < gm; ++i)
+    for (int64_t j = 0; j < gn; ++j)
+      if (!(j * TDN + TDN - 1 < i * TDM)) ++cnt;
+  return cnt;
+}
+
+inline int tn_nsplit(int64_t rows, int64_t M, int64_t N, int upper_only = 0) {
+  const int64_t tiles = tn_tiles(M, N, upper_only);
   int64_t want = (4 * 148 + tiles - 1) / tiles;           // ~4 CTAs per SM in total
   const int64_t maxs = (rows + 255) / 256;                // at least 256 rows per split
   if (want > maxs) want = maxs;
@@ -326,42 +487,195 @@ inline int tn_nsplit(int64_t rows, int64_t M, int64_t N) {
   return static_cast<int>(want);
 }
 
-// C (M x N, ldc) = A^T B ; partials must hold nsplit*M*N doubles
+bool g_tn_attr[64] = {};
+
+// C (M x N, ldc) = A^T B [Tm] ; partials must hold nsplit*M*N doubles
 int launch_tn(double* C, int64_t ldc, const double* A, int64_t lda, const double* B, int64_t ldb, int64_t rows, int64_t M,
-              int64_t N, double* partials, cudaStream_t st) {
+              int64_t N, double* partials, int upper_only, const double* Tm, int64_t ldt, cudaStream_t st) {
   if (M <= 0 || N <= 0) return NPW_OK;
-  const int ns = tn_nsplit(rows, M, N);
-  const int kchunk = static_cast<int>((rows + ns - 1) / ns);
-  dim3 grid(static_cast<unsigned>((N + TT - 1) / TT), static_cast<unsigned>((M + TT - 1) / TT), static_cast<unsigned>(ns));
-  tn_partial_kernel<<<grid, 256, 0, st>>>(partials, A, lda, B, ldb, static_cast<int>(rows), static_cast<int>(M),
-                                          static_cast<int>(N), kchunk);
+  const int ns = tn_nsplit(rows, M, N, upper_only);
+  const int kchunk = static_cast<int>((((rows + ns - 1) / ns) + TDK - 1) / TDK * TDK);
+  if (aligned16(A, lda) && aligned16(B, ldb)) {
+    int dev = 0;
+    NPW_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 64 && !g_tn_attr[dev]) {
+      NPW_CUDA_CHECK(cudaFuncSetAttribute(tn_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TD_SMEM));
+      g_tn_attr[dev] = true;
+    }
+    dim3 grid(static_cast<unsigned>((N + TDN - 1) / TDN), static_cast<unsigned>((M + TDM - 1) / TDM), static_cast<unsigned>(ns));
+    tn_dmma_kernel<<<grid, 256, TD_SMEM, st>>>(partials, A, lda, B, ldb, static_cast<int>(rows), static_cast<int>(M),
+                                               static_cast<int>(N), kchunk, upper_only);
+  } else {
+    dim3 grid(static_cast<unsigned>((N + TT - 1) / TT), static_cast<unsigned>((M + TT - 1) / TT), static_cast<unsigned>(ns));
+    tn_partial_kernel<<<grid, 256, 0, st>>>(partials, A, lda, B, ldb, static_cast<int>(rows), static_cast<int>(M),
+                                            static_cast<int>(N), kchunk);
+  }
   NPW_LAUNCH_CHECK();
   const int64_t total = M * N;
-  int rb = static_cast<int>((total + 255) / 256);
+  int rb = Tm ? static_cast<int>((M + 7) / 8) : static_cast<int>((total + 255) / 256);
   if (rb > 148 * 8) rb = 148 * 8;
-  tn_reduce_kernel<<<rb, 256, 0, st>>>(C, ldc, partials, static_cast<int>(M), static_cast<int>(N), ns);
+  tn_reduce_kernel<<<rb, 256, 0, st>>>(C, ldc, partials, static_cast<int>(M), static_cast<int>(N), ns, Tm, ldt);
   NPW_LAUNCH_CHECK();
   return NPW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Streaming rank-k update (k <= 32) of the trailing columns:  C[r][c] -= sum_q V[r][q] W[c][q]
+// (C rows x nt, V rows x k = the panel's reflectors, W nt x k = Wt T_p).  64 x 64 tile per CTA, 8 warps of 32 x 16,
+// operands staged k-contiguous with rows padded to 36 doubles (conflict-free fragment loads), DMMA.  Every element of C
+// is read and written exactly once and gets 2 x 32 flop: HBM-bound (the tensor pipe would sustain ~1.4x the traffic).
+// The C fragments are requested before the operands are staged so that the loads overlap the staging and the math.
+// ------------------------------------------------------------------------------------------------
+constexpr int RU = 64, RU_LD = QW + 4;
+
+__global__ void __launch_bounds__(256) rank_update_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ V,
+                                                          int64_t ldv, const double* __restrict__ W, int64_t ldw, int rows, int nt,
+                                                          int k, int vec) {
+  __shared__ __align__(16) double Vs[RU][RU_LD];
+  __shared__ __align__(16) double Ws[RU][RU_LD];
+  const int r0 = blockIdx.y * RU, c0 = blockIdx.x * RU;
+  const int t = threadIdx.x;
+  const int warp = t >> 5, lane = t & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;                  // warp tile: rows 32 wm.., cols 16 wn..
+  // ---- this lane's C fragments: rows r0 + 32 wm + 8 i + g, cols c0 + 16 wn + 8 j + 2 c + {0, 1}
+  double2 cf[4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 32 * wm + 8 * i + g;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int col = c0 + 16 * wn + 8 * j + 2 * c;
+      double2 v = make_double2(0.0, 0.0);
+      if (r < rows) {
+        const double* src = C + static_cast<int64_t>(r) * ldc + col;
+        if (vec && col + 1 < nt) v = *reinterpret_cast<const double2*>(src);
+        else {
+          if (col < nt) v.x = src[0];
+          if (col + 1 < nt) v.y = src[1];
+        }
+      }
+      cf[i][j] = v;
+    }
+  }
+  // ---- stage V (64 x 32) and W (64 x 32), zero padded
+  for (int e = t; e < RU * QW; e += 256) {
+    const int rr = e >> 5, q = e & 31;
+    Vs[rr][q] = (r0 + rr < rows && q < k) ? V[static_cast<int64_t>(r0 + rr) * ldv + q] : 0.0;
+    Ws[rr][q] = (c0 + rr < nt && q < k) ? W[static_cast<int64_t>(c0 + rr) * ldw + q] : 0.0;
+  }
+  __syncthreads();
+  double acc[4][2][2] = {};
+#pragma unroll
+  for (int ks = 0; ks < QW / 4; ++ks) {
+    double a[4], b[2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[i] = Vs[32 * wm + 8 * i + g][4 * ks + c];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) b[j] = Ws[16 * wn + 8 * j + g][4 * ks + c];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + 32 * wm + 8 * i + g;
+    if (r >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int col = c0 + 16 * wn + 8 * j + 2 * c;
+      double* dst = C + static_cast<int64_t>(r) * ldc + col;
+      const double2 o = make_double2(cf[i][j].x - acc[i][j][0], cf[i][j].y - acc[i][j][1]);
+      if (vec && col + 1 < nt) *reinterpret_cast<double2*>(dst) = o;
+      else {
+        if (col < nt) dst[0] = o.x;
+        if (col + 1 < nt) dst[1] = o.y;
+      }
+    }
+  }
+}
+
+int launch_rank_update(double* C, int64_t ldc, const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t rows,
+                       int64_t nt, int k, cudaStream_t st) {
+  if (rows <= 0 || nt <= 0 || k <= 0) return NPW_OK;
+  dim3 grid(static_cast<unsigned>((nt + RU - 1) / RU), static_cast<unsigned>((rows + RU - 1) / RU));
+  rank_update_kernel<<<grid, 256, 0, st>>>(C, ldc, V, ldv, W, ldw, static_cast<int>(rows), static_cast<int>(nt), k,
+                                           aligned16(C, ldc) ? 1 : 0);
+  NPW_LAUNCH_CHECK();
+  return NPW_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Off-diagonal block column of T for the panel at j0 (w columns), dlarft's recurrence in block form:
+//   T[0:j0, j0:j0+w] = -T[0:j0, 0:j0] (G[0:j0, j0:j0+w] T_pp),   G = V^T V (upper part), T_pp = T[j0:j0+w, j0:j0+w].
+// CTA rb computes output rows [32 rb, 32 rb + 32): T is upper triangular, so only k-blocks kb >= rb contribute.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) t_offdiag_kernel(double* __restrict__ T, int64_t ldt, const double* __restrict__ Gm,
+                                                        int64_t ldg, int j0, int w) {
+  __shared__ double sTpp[QW][QW + 1];
+  __shared__ double sG[QW][QW + 1];
+  __shared__ double sX[QW][QW + 1];     // G_blk T_pp
+  __shared__ double sTl[QW][QW + 1];    // T[32 rb.., 32 kb..]
+  const int rb = blockIdx.x;
+  const int t = threadIdx.x;
+  const int ty = t >> 5, tx = t & 31;   // 8 x 32: thread owns rows ty, ty + 8, ty + 16, ty + 24 of column tx
+  for (int e = t; e < QW * QW; e += 256) {
+    const int i = e >> 5, cc = e & 31;
+    sTpp[i][cc] = (i < w && cc < w) ? T[static_cast<int64_t>(j0 + i) * ldt + j0 + cc] : 0.0;
+  }
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  const int nkb = (j0 + QW - 1) / QW;
+  for (int kb = rb; kb < nkb; ++kb) {
+    __syncthreads();
+    for (int e = t; e < QW * QW; e += 256) {
+      const int i = e >> 5, cc = e & 31;
+      const int gr = kb * QW + i;
+      sG[i][cc] = (gr < j0 && cc < w) ? Gm[static_cast<int64_t>(gr) * ldg + j0 + cc] : 0.0;
+      const int tr = rb * QW + i, tc = kb * QW + cc;
+      sTl[i][cc] = (tr < j0 && tc < j0) ? T[static_cast<int64_t>(tr) * ldt + tc] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = ty + 8 * u;
+      double x = 0.0;
+#pragma unroll 8
+      for (int q = 0; q < QW; ++q) x = fma(sG[i][q], sTpp[q][tx], x);
+      sX[i][tx] = x;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = ty + 8 * u;
+      double a = acc[u];
+#pragma unroll 8
+      for (int q = 0; q < QW; ++q) a = fma(sTl[i][q], sX[q][tx], a);
+      acc[u] = a;
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int r = rb * QW + ty + 8 * u;
+    if (r < j0 && tx < w) T[static_cast<int64_t>(r) * ldt + j0 + tx] = -acc[u];
+  }
 }
 
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
 struct QrWork {
-  size_t scratch, tau, wt, tmp, gram, partials, total;
+  size_t scratch, tau, tmp, gram, partials, total;
 };
 
 QrWork qr_work_layout(int64_t m, int64_t n) {
   QrWork w;
   size_t off = 0;
-  w.scratch = off; off += align256(2 * SCR_STRIDE * sizeof(double));
+  w.scratch = off; off += align256(PK_BYTES + 256);                                   // packets + error word
   w.tau = off; off += align256(static_cast<size_t>(n) * sizeof(double));
-  w.wt = off; off += align256(static_cast<size_t>(n) * QW * sizeof(double));         // Wt: (n - j0 - w) x w
-  w.tmp = off; off += align256(static_cast<size_t>(n) * QW * sizeof(double));        // Wt T_p  /  G T_pp
+  w.tmp = off; off += align256(static_cast<size_t>(n) * QW * sizeof(double));        // Wt T_p
   w.gram = off; off += align256(static_cast<size_t>(n) * n * sizeof(double));        // G = V^T V
-  const int ns_g = tn_nsplit(m, n, n), ns_w = tn_nsplit(m, n, QW);
+  const int ns_g = tn_nsplit(m, n, n, 1);
   size_t pb = static_cast<size_t>(ns_g) * n * n;
-  const size_t pw = static_cast<size_t>(ns_w) * n * QW;
-  if (pw > pb) pb = pw;
   // nsplit depends on the row count of each call; bound it by the largest value tn_nsplit can return for these widths
   const size_t pmax = static_cast<size_t>(256) * n * QW;
   if (pmax > pb) pb = pmax;
@@ -400,9 +714,9 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const QrWork wl = qr_work_layout(m, n);
   char* wb = static_cast<char*>(work);
-  double* scratch = reinterpret_cast<double*>(wb + wl.scratch);
+  uint64_t* packets = reinterpret_cast<uint64_t*>(wb + wl.scratch);
+  int* err = reinterpret_cast<int*>(wb + wl.scratch + PK_BYTES);
   double* tau = reinterpret_cast<double*>(wb + wl.tau);
-  double* Wt = reinterpret_cast<double*>(wb + wl.wt);
   double* tmp = reinterpret_cast<double*>(wb + wl.tmp);
   double* gram = reinterpret_cast<double*>(wb + wl.gram);
   double* partials = reinterpret_cast<double*>(wb + wl.partials);
@@ -417,17 +731,28 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
       set_error("device does not support cooperative launch");
       return NPW_ERR_UNSUPPORTED;
     }
-    NPW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_panel_kernel<false>, QTHREADS, 0));
     NPW_CUDA_CHECK(cudaFuncSetAttribute(qr_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         QR_SMEM_ROWS * QW * static_cast<int>(sizeof(double))));
+    NPW_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, qr_panel_kernel<true>, QTHREADS,
+                                                               QR_SMEM_ROWS * QW * sizeof(double)));
     int g = sms * (per_sm > 0 ? 1 : 0);
     if (g > MAX_GRID) g = MAX_GRID;
-    if (g < 1) g = 1;
+    if (const char* e = getenv("NPW_B200_QR_GRID")) {       // tuning knob: CTAs of a panel launch
+      const int v = atoi(e);
+      if (v >= 1 && v < g) g = v;
+    }
+    if (g < 1) {
+      set_error("qr_panel_kernel does not fit on an SM");
+      return NPW_ERR_UNSUPPORTED;
+    }
     g_coop_grid[dev] = g;
   }
   const int max_grid = dev < 64 ? g_coop_grid[dev] : 1;
 
   int rc;
+  // the all-gather packets validate themselves by sequence number: start every factorisation from zeroed packets
+  // (sequence numbers are unique within a factorisation and never 0)
+  NPW_CUDA_CHECK(cudaMemsetAsync(packets, 0, PK_BYTES + 256, st));
   if (V != A) {
     rc = launch_copy2d(V, ldv, A, lda, m, n, 0, st);
     if (rc) return rc;
@@ -437,12 +762,14 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
   rc = launch_fill2d(T, ldt, n, n, 0, 0.0, st);
   if (rc) return rc;
 
+  uint32_t seq = 1;
   for (int64_t j0 = 0; j0 < n; j0 += QW) {
     const int w = static_cast<int>(n - j0 < QW ? n - j0 : QW);
     const int64_t rows = m - j0;
     PanelArgs pa;
     pa.V = V; pa.ldv = ldv; pa.m = static_cast<int>(m); pa.j0 = static_cast<int>(j0); pa.w = w;
-    pa.R = R; pa.ldr = ldr; pa.T = T; pa.ldt = ldt; pa.tau = tau; pa.scratch = scratch;
+    pa.R = R; pa.ldr = ldr; pa.T = T; pa.ldt = ldt; pa.tau = tau; pa.packets = packets; pa.seq0 = seq; pa.err = err;
+    seq += QW + 2;                                          // steps 0 .. w of this launch
     int g = static_cast<int>((rows + 127) / 128);           // >= 128 panel rows per CTA
     if (g > max_grid) g = max_grid;
     if (g < 1) g = 1;
@@ -459,14 +786,11 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
     if (nt > 0) {
       double* C = V + j0 * ldv + j0 + w;                    // rows x nt, starts at row j0
       const double* Vp = V + j0 * ldv + j0;                 // rows x w (explicit unit-lower after the panel kernel)
-      // Wt = C^T V_p  (nt x w)
-      rc = launch_tn(Wt, QW, C, ldv, Vp, ldv, rows, nt, w, partials, st);
-      if (rc) return rc;
-      // tmp = Wt T_p  (applying Q^T = I - V T^T V^T:  C -= V (T^T (V^T C))  <=>  C -= V (Wt T)^T)
-      rc = launch_gemm(tmp, QW, nullptr, 0, Wt, QW, 0, T + j0 * ldt + j0, ldt, 0, nt, w, w, 1.0, 0.0, 0, st);
+      // tmp = (C^T V_p) T_p  (nt x w): applying Q^T = I - V T^T V^T is  C -= V (T^T (V^T C))  <=>  C -= V ((C^T V) T)^T
+      rc = launch_tn(tmp, QW, C, ldv, Vp, ldv, rows, nt, w, partials, 0, T + j0 * ldt + j0, ldt, st);
       if (rc) return rc;
       // C -= V_p tmp^T
-      rc = launch_gemm(C, ldv, C, ldv, Vp, ldv, 0, tmp, QW, 1, rows, nt, w, -1.0, 1.0, 0, st);
+      rc = launch_rank_update(C, ldv, Vp, ldv, tmp, QW, rows, nt, w, st);
       if (rc) return rc;
       // rows j0 .. j0+w-1 of the trailing columns are final rows of R
       rc = launch_copy2d(R + j0 * ldr + j0 + w, ldr, C, ldv, w, nt, 0, st);
@@ -476,18 +800,14 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
   // explicit V: zero strictly above the diagonal (the panel kernel already wrote the unit diagonal)
   rc = launch_fill2d(V, ldv, n, n, 2, 0.0, st);
   if (rc) return rc;
-  // off-diagonal blocks of T from the Gram matrix of V
+  // off-diagonal blocks of T from the Gram matrix of V (upper tiles)
   if (n > QW) {
-    rc = launch_tn(gram, n, V, ldv, V, ldv, m, n, n, partials, st);
+    rc = launch_tn(gram, n, V, ldv, V, ldv, m, n, n, partials, 1, nullptr, 0, st);
     if (rc) return rc;
     for (int64_t j0 = QW; j0 < n; j0 += QW) {
       const int w = static_cast<int>(n - j0 < QW ? n - j0 : QW);
-      // tmp (j0 x w) = G[0:j0, panel] T_pp
-      rc = launch_gemm(tmp, QW, nullptr, 0, gram + j0, n, 0, T + j0 * ldt + j0, ldt, 0, j0, w, w, 1.0, 0.0, 0, st);
-      if (rc) return rc;
-      // T[0:j0, panel] = -T[0:j0, 0:j0] tmp
-      rc = launch_gemm(T + j0, ldt, nullptr, 0, T, ldt, 0, tmp, QW, 0, j0, w, j0, -1.0, 0.0, 0, st);
-      if (rc) return rc;
+      t_offdiag_kernel<<<static_cast<unsigned>((j0 + QW - 1) / QW), 256, 0, st>>>(T, ldt, gram, n, static_cast<int>(j0), w);
+      NPW_LAUNCH_CHECK();
     }
   }
   return NPW_OK;
