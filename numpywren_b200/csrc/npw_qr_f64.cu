@@ -38,9 +38,13 @@ constexpr int QWARPS = QTHREADS / 32;
 constexpr int MAX_GRID = 160;     // upper bound on the CTAs of a panel launch (<= SM count)
 constexpr int QMAXQ = (MAX_GRID + QWARPS - 1) / QWARPS;   // vectors one reader group adds per step
 
-// packet scratch, per step parity: [MAX_GRID][32 doubles x 2 packets] partial vectors, then [32 x 2] the pivot row
+// packet scratch, per step parity: [MAX_GRID][32 doubles x 2 packets] partial vectors, [32 x 2] the pivot row, then
+// [QMAXGROUPS][32 x 2] group sums
 constexpr int PK_PER_VEC = 2 * QW;
-constexpr int PK_STRIDE = (MAX_GRID + 1) * PK_PER_VEC;
+constexpr int QGSZ = 12;                                   // CTAs per group of the two-level gather (register-resident kernel)
+constexpr int QMAXGROUPS = (MAX_GRID + QGSZ - 1) / QGSZ;   // 14
+constexpr int PK_GROUP0 = MAX_GRID + 1;                    // group sums live behind the per-CTA vectors and the pivot row
+constexpr int PK_STRIDE = (MAX_GRID + 1 + QMAXGROUPS) * PK_PER_VEC;
 constexpr size_t PK_BYTES = 2 * static_cast<size_t>(PK_STRIDE) * sizeof(uint64_t);
 constexpr long long QR_SPIN_LIMIT = 4000000000ll;          // ~2 s of polling: give up (sets *err) instead of hanging
 
@@ -265,6 +269,243 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(PanelArgs p) {
   if (SMEM) {                                        // write the factored chunk back (V below the diagonal, explicit unit/zeros)
     for (int r = r_lo + warp; r < r_hi; r += QWARPS)
       if (lane_ok) Vp[static_cast<int64_t>(r) * p.ldv + lane] = s_chunk[static_cast<size_t>(r - r_lo) * QW + lane];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Register-resident variant of the panel kernel (the one a TSQR leaf uses): 8 warps, every warp keeps its RPW rows of
+// the panel (lane = column) in registers for all 32 column steps, so a pass is shuffles and DFMAs only — no shared
+// memory traffic, fully unrolled and branch-free, hence ILP across the rows of a warp.  A CTA holds up to
+// 8 x RPW = 448 rows (65536 rows over 148 CTAs = 443).  Same arithmetic, same order of additions inside a warp's
+// partial sums as the shared-memory variant up to the 4-way split of the accumulator; same all-gather protocol.
+// ------------------------------------------------------------------------------------------------
+constexpr int RTHREADS = 256, RWARPS = 8, RPW = 56;
+constexpr int RPIV = QW / RWARPS + 1;   // register rows of a warp that can be (or sit directly below) a pivot row of the launch
+
+__global__ void __launch_bounds__(RTHREADS, 1) qr_panel_reg_kernel(PanelArgs p) {
+  const int G = gridDim.x;
+  const int cta = blockIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int rows = p.m - p.j0;
+  const int per = (rows + G - 1) / G;                // <= RWARPS * RPW (host guarantees)
+  const int r_lo = p.j0 + cta * per;
+  const int r_hi = min(p.m, r_lo + per);
+  const int w = p.w;
+  const bool lane_ok = lane < w;
+  double* Vp = p.V + p.j0;
+
+  __shared__ double s_part[RWARPS][QW];
+  __shared__ double s_red[RWARPS][QW];
+  __shared__ double s_red2[RWARPS][QW];
+  __shared__ double s_T[QW][QW + 1];
+  __shared__ double s_Z[QW][QW];
+  __shared__ double s_tau[QW];
+
+  for (int e = threadIdx.x; e < QW * (QW + 1); e += RTHREADS) (&s_T[0][0])[e] = 0.0;
+
+  // row i of this warp: global row r_lo + warp + RWARPS * i
+  double v[RPW];
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = r_lo + warp + RWARPS * i;
+    v[i] = (r < r_hi && lane_ok) ? Vp[static_cast<int64_t>(r) * p.ldv + lane] : 0.0;
+  }
+
+  auto publish = [&](int step, double s) {            // warp 0: this CTA's vector for step `step`
+    uint64_t* base = p.packets + static_cast<size_t>(step & 1) * PK_STRIDE;
+    ll_store(base + static_cast<size_t>(cta) * PK_PER_VEC + 2 * lane, s, p.seq0 + static_cast<uint32_t>(step));
+  };
+  auto publish_row = [&](int step, int prow) {        // the warp that holds row `prow` publishes it (pivot row of `step`)
+    if (prow < r_lo || prow >= r_hi || ((prow - r_lo) & (RWARPS - 1)) != warp) return;
+    const int ip = (prow - r_lo) / RWARPS;
+    double val = 0.0;
+#pragma unroll
+    for (int i = 0; i < RPIV; ++i) val = (i == ip) ? v[i] : val;   // pivot rows are among the CTA's first 32 + 1 rows
+    uint64_t* base = p.packets + static_cast<size_t>(step & 1) * PK_STRIDE;
+    ll_store(base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane, val, p.seq0 + static_cast<uint32_t>(step));
+  };
+  // Two-level all-gather: the first CTA of every group of QGSZ adds its group's vectors and publishes the group sum;
+  // everybody adds the <= QMAXGROUPS group sums.  A thread polls at most three packets per sweep (round 2a read all 148
+  // vectors in every CTA: 78 KB per CTA per sweep kept the L2 busy and a sweep took ~1 us).
+  const int grp_id = cta / QGSZ;
+  const bool leader = cta % QGSZ == 0;
+  const int grp_cnt = min(QGSZ, G - grp_id * QGSZ);
+  const int ngroups = (G + QGSZ - 1) / QGSZ;
+  // poll up to three packets (slot pointers may be null = absent) until all present ones carry `seq`
+  auto poll3 = [&](const uint64_t* s0, const uint64_t* s1, const uint64_t* s2, uint32_t seq, double& v0, double& v1, double& v2) {
+    uint64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0;
+    const long long t0 = clock64();
+    bool ok = *static_cast<volatile int*>(p.err) != 0;
+    while (!ok) {
+      if (s0) ll_load(s0, a0, a1);
+      if (s1) ll_load(s1, b0, b1);
+      if (s2) ll_load(s2, c0, c1);
+      ok = (!s0 || ll_valid(a0, a1, seq)) && (!s1 || ll_valid(b0, b1, seq)) && (!s2 || ll_valid(c0, c1, seq));
+      if (!ok && clock64() - t0 > QR_SPIN_LIMIT) {
+        *static_cast<volatile int*>(p.err) = 1;
+        break;
+      }
+    }
+    v0 = s0 ? ll_value(a0, a1) : 0.0;
+    v1 = s1 ? ll_value(b0, b1) : 0.0;
+    v2 = s2 ? ll_value(c0, c1) : 0.0;
+  };
+  auto gather = [&](int step, bool need_pivot, double& g_l, double& prow_l) {
+    const uint64_t* base = p.packets + static_cast<size_t>(step & 1) * PK_STRIDE;
+    const uint32_t seq = p.seq0 + static_cast<uint32_t>(step);
+    if (leader) {                                           // CTA-uniform
+      const int m0 = warp, m1 = warp + RWARPS;
+      double v0, v1, v2;
+      poll3(m0 < grp_cnt ? base + static_cast<size_t>(grp_id * QGSZ + m0) * PK_PER_VEC + 2 * lane : nullptr,
+            m1 < grp_cnt ? base + static_cast<size_t>(grp_id * QGSZ + m1) * PK_PER_VEC + 2 * lane : nullptr, nullptr, seq, v0, v1, v2);
+      s_red2[warp][lane] = v0 + v1;
+      __syncthreads();
+      if (warp == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int q = 0; q < RWARPS; ++q) t += s_red2[q][lane];
+        ll_store(const_cast<uint64_t*>(base) + static_cast<size_t>(PK_GROUP0 + grp_id) * PK_PER_VEC + 2 * lane, t, seq);
+      }
+    }
+    const int g0 = warp, g1 = warp + RWARPS;
+    double v0, v1;
+    poll3(g0 < ngroups ? base + static_cast<size_t>(PK_GROUP0 + g0) * PK_PER_VEC + 2 * lane : nullptr,
+          g1 < ngroups ? base + static_cast<size_t>(PK_GROUP0 + g1) * PK_PER_VEC + 2 * lane : nullptr,
+          need_pivot ? base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane : nullptr, seq, v0, v1, prow_l);
+    s_red[warp][lane] = v0 + v1;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < RWARPS; ++q) t += s_red[q][lane];
+    g_l = t;
+  };
+  auto block_sum_and_publish = [&](int step, double acc) {
+    s_part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q < RWARPS; ++q) s += s_part[q][lane];
+      publish(step, s);
+    }
+  };
+
+  // ---- initial partials for column 0: g[c] = sum_{r > j0} x_r * P[r][c], x = column 0
+  {
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int i = 0; i < RPW; ++i) {
+      const int r = r_lo + warp + RWARPS * i;
+      const double x = __shfl_sync(0xffffffffu, v[i], 0);
+      a4[i & 3] = fma(r > p.j0 ? x : 0.0, v[i], a4[i & 3]);
+    }
+    publish_row(0, p.j0);
+    block_sum_and_publish(0, (a4[0] + a4[1]) + (a4[2] + a4[3]));
+  }
+
+  for (int j = 0; j < w; ++j) {
+    const int gj = p.j0 + j;
+    double g_l, prow_l;
+    gather(j, true, g_l, prow_l);
+    if (j > 0 && cta == 0 && warp == 1) s_Z[j - 1][lane] = g_l;
+    const double alpha = __shfl_sync(0xffffffffu, prow_l, j);
+    const double xn2 = __shfl_sync(0xffffffffu, g_l, j);
+    double tau = 0.0, scale = 0.0, beta = alpha;
+    if (xn2 > 0.0) {
+      const double nrm = sqrt(alpha * alpha + xn2);
+      beta = alpha >= 0.0 ? -nrm : nrm;
+      tau = (beta - alpha) / beta;
+      scale = 1.0 / (alpha - beta);
+    }
+    if (threadIdx.x == 0) s_tau[j] = tau;
+    const double wc = (lane > j && lane_ok) ? prow_l + scale * g_l : 0.0;
+    const double tw = tau * wc;
+    const bool right = lane > j, diag = lane == j, left = lane < j;
+    const bool next = j + 1 < w;
+    // per-lane constants that turn the column roles into arithmetic: new = v * kv + v_j[r] * cv
+    //   lane > j: v - v_j[r] tau w_c      lane == j: v_j[r]      lane < j: v (finished columns of V)
+    const double kv = diag ? 0.0 : 1.0;
+    const double cv = diag ? 1.0 : (right ? -tw : 0.0);
+
+    double a4[4] = {0.0, 0.0, 0.0, 0.0};
+    // Each row adds, per lane: lane < j: V[r][i] v_j[r] (Gram); lane > j: x'_r P'[r][c] (dot products of column j+1, rows
+    // below the next pivot).  Lane j itself collects a product nobody reads (the gathers use lanes != j only).
+    if (r_lo > p.j0 + w) {
+      // no pivot row in this CTA during this launch: every row is below the pivots (padding rows are all zero)
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const double x = __shfl_sync(0xffffffffu, v[i], j);
+        const double vr = x * scale;                  // v_j[r]
+        const double nv = fma(vr, cv, v[i] * kv);
+        v[i] = nv;
+        const double xn = __shfl_sync(0xffffffffu, nv, (j + 1) & 31);
+        a4[i & 3] = fma(nv, left ? vr : xn, a4[i & 3]);
+      }
+    } else {
+      // This CTA holds pivot rows of this launch.  They are among its first 32 rows (r_lo >= j0), i.e. register rows
+      // i < RPIV of some warp: only those need the predicates; rows at or above the pivot get v_j[r] = 0 (nothing
+      // changes; column j of a finished row is already 0).
+#pragma unroll
+      for (int i = 0; i < RPW; ++i) {
+        const int r = r_lo + warp + RWARPS * i;
+        const double x = __shfl_sync(0xffffffffu, v[i], j);
+        const double vr = (i >= RPIV || r > gj) ? x * scale : 0.0;
+        const double nv = fma(vr, cv, v[i] * kv);
+        v[i] = nv;
+        const double xn = __shfl_sync(0xffffffffu, nv, (j + 1) & 31);
+        a4[i & 3] = fma(nv, left ? vr : ((i >= RPIV || r > gj + 1) ? xn : 0.0), a4[i & 3]);
+      }
+      // ---- pivot row (one warp of one CTA): R(gj, c) = P[gj][c] - tau w_c, diagonal beta; the row of V becomes e_j
+      // (the loop above left its lanes != j untouched)
+      if (gj >= r_lo && gj < r_hi && ((gj - r_lo) & (RWARPS - 1)) == warp) {
+        const int ip = (gj - r_lo) / RWARPS;
+        double pv = 0.0;
+#pragma unroll
+        for (int i = 0; i < RPIV; ++i) pv = (i == ip) ? v[i] : pv;
+        if (left) a4[0] += pv;                        // Gram contribution v_i[gj] * 1
+        if (right) pv -= tw;
+        if (diag) pv = beta;
+        if (lane_ok && !left) p.R[static_cast<int64_t>(gj) * p.ldr + p.j0 + lane] = pv;
+        const double nv = diag ? 1.0 : 0.0;
+#pragma unroll
+        for (int i = 0; i < RPIV; ++i) v[i] = (i == ip && !left) ? nv : v[i];
+      }
+    }
+    if (next) publish_row(j + 1, gj + 1);
+    block_sum_and_publish(j + 1, (a4[0] + a4[1]) + (a4[2] + a4[3]));
+  }
+  {
+    double g_l, prow_l;
+    gather(w, false, g_l, prow_l);
+    if (cta == 0 && warp == 1) {
+      s_Z[w - 1][lane] = g_l;
+      __syncwarp();
+      for (int jj = 0; jj < w; ++jj) {
+        const double tj = s_tau[jj];
+        double t = 0.0;
+        if (lane < jj)
+          for (int q = lane; q < jj; ++q) t = fma(s_T[lane][q], s_Z[jj][q], t);
+        if (lane < jj) s_T[lane][jj] = -tj * t;
+        if (lane == jj) s_T[jj][jj] = tj;
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+  if (cta == 0) {
+    for (int e = threadIdx.x; e < w * w; e += RTHREADS) {
+      const int i = e / w, c = e - i * w;
+      p.T[static_cast<int64_t>(p.j0 + i) * p.ldt + p.j0 + c] = (c >= i) ? s_T[i][c] : 0.0;
+    }
+    for (int e = threadIdx.x; e < w; e += RTHREADS) p.tau[p.j0 + e] = s_tau[e];
+    if (threadIdx.x == 0 && *static_cast<volatile int*>(p.err) != 0)
+      p.T[static_cast<int64_t>(p.j0) * p.ldt + p.j0] = __longlong_as_double(0x7ff8000000000000ll);
+  }
+#pragma unroll
+  for (int i = 0; i < RPW; ++i) {
+    const int r = r_lo + warp + RWARPS * i;
+    if (r < r_hi && lane_ok) Vp[static_cast<int64_t>(r) * p.ldv + lane] = v[i];
   }
 }
 
@@ -527,81 +768,153 @@ int launch_tn(double* C, int64_t ldc, const double* A, int64_t lda, const double
 // The C fragments are requested before the operands are staged so that the loads overlap the staging and the math.
 // ------------------------------------------------------------------------------------------------
 constexpr int RU = 64, RU_LD = QW + 4;
+constexpr int RU_SMEM = 3 * RU * RU_LD * static_cast<int>(sizeof(double));   // V tile + double-buffered W tile
 
-__global__ void __launch_bounds__(256) rank_update_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ V,
-                                                          int64_t ldv, const double* __restrict__ W, int64_t ldw, int rows, int nt,
-                                                          int k, int vec) {
-  __shared__ __align__(16) double Vs[RU][RU_LD];
-  __shared__ __align__(16) double Ws[RU][RU_LD];
-  const int r0 = blockIdx.y * RU, c0 = blockIdx.x * RU;
+// A CTA owns a 64-row stripe of C and walks over `tiles_per_cta` column tiles of 64: the V tile is staged once, the W
+// tile of the next column tile and the next C fragments are requested before the current tile is multiplied, so the
+// HBM stream never waits for the math.
+__global__ void __launch_bounds__(256, 2) rank_update_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ V,
+                                                             int64_t ldv, const double* __restrict__ W, int64_t ldw, int rows, int nt,
+                                                             int k, int vec, int vecv, int tiles_per_cta) {
+  extern __shared__ __align__(16) double ru_smem[];
+  double* Vs = ru_smem;                                     // [RU][RU_LD]
+  double* Ws = ru_smem + RU * RU_LD;                        // [2][RU][RU_LD]
+  const int r0 = blockIdx.x * RU;
+  const int nct = (nt + RU - 1) / RU;
+  const int ct0 = blockIdx.y * tiles_per_cta;
+  const int ct1 = min(nct, ct0 + tiles_per_cta);
+  if (ct0 >= ct1) return;
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
   const int g = lane >> 2, c = lane & 3;
   const int wm = warp >> 2, wn = warp & 3;                  // warp tile: rows 32 wm.., cols 16 wn..
-  // ---- this lane's C fragments: rows r0 + 32 wm + 8 i + g, cols c0 + 16 wn + 8 j + 2 c + {0, 1}
-  double2 cf[4][2];
+
+  // this lane's C fragments of column tile ct: rows r0 + 32 wm + 8 i + g, cols 64 ct + 16 wn + 8 j + 2 c + {0, 1}
+  auto load_c = [&](int ct, double2 (&cf)[4][2]) {
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + 32 * wm + 8 * i + g;
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 32 * wm + 8 * i + g;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int col = c0 + 16 * wn + 8 * j + 2 * c;
+      for (int j = 0; j < 2; ++j) {
+        const int col = ct * RU + 16 * wn + 8 * j + 2 * c;
+        double2 v = make_double2(0.0, 0.0);
+        if (r < rows) {
+          const double* src = C + static_cast<int64_t>(r) * ldc + col;
+          if (vec && col + 1 < nt) v = *reinterpret_cast<const double2*>(src);
+          else {
+            if (col < nt) v.x = src[0];
+            if (col + 1 < nt) v.y = src[1];
+          }
+        }
+        cf[i][j] = v;
+      }
+    }
+  };
+  // a 64 x 32 operand tile (row stride ld) as 4 double2 per thread
+  auto fetch_tile = [&](const double* M, int64_t ld, int row0, int nrows, int aligned, double2 (&wr)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = t + 256 * u;
+      const int rr = row0 + (e >> 4), q = 2 * (e & 15);
       double2 v = make_double2(0.0, 0.0);
-      if (r < rows) {
-        const double* src = C + static_cast<int64_t>(r) * ldc + col;
-        if (vec && col + 1 < nt) v = *reinterpret_cast<const double2*>(src);
+      if (rr < nrows) {
+        const double* src = M + static_cast<int64_t>(rr) * ld + q;
+        if (aligned && q + 1 < k) v = *reinterpret_cast<const double2*>(src);
         else {
-          if (col < nt) v.x = src[0];
-          if (col + 1 < nt) v.y = src[1];
+          if (q < k) v.x = src[0];
+          if (q + 1 < k) v.y = src[1];
         }
       }
-      cf[i][j] = v;
+      wr[u] = v;
     }
-  }
-  // ---- stage V (64 x 32) and W (64 x 32), zero padded
-  for (int e = t; e < RU * QW; e += 256) {
-    const int rr = e >> 5, q = e & 31;
-    Vs[rr][q] = (r0 + rr < rows && q < k) ? V[static_cast<int64_t>(r0 + rr) * ldv + q] : 0.0;
-    Ws[rr][q] = (c0 + rr < nt && q < k) ? W[static_cast<int64_t>(c0 + rr) * ldw + q] : 0.0;
-  }
+  };
+  auto stage_tile = [&](double* dst, const double2 (&wr)[4]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = t + 256 * u;
+      *reinterpret_cast<double2*>(dst + (e >> 4) * RU_LD + 2 * (e & 15)) = wr[u];
+    }
+  };
+
+  double2 cf[4][2], cfn[4][2], wr[4];
+  load_c(ct0, cf);
+  fetch_tile(V, ldv, r0, rows, vecv, wr);
+  stage_tile(Vs, wr);
+  fetch_tile(W, ldw, ct0 * RU, nt, 1, wr);
+  stage_tile(Ws, wr);
   __syncthreads();
-  double acc[4][2][2] = {};
+  int buf = 0;
+  for (int ct = ct0; ct < ct1; ++ct) {
+    const bool more = ct + 1 < ct1;
+    if (more) {
+      fetch_tile(W, ldw, (ct + 1) * RU, nt, 1, wr);
+      load_c(ct + 1, cfn);
+    }
+    const double* Wb = Ws + buf * RU * RU_LD;
+    double acc[4][2][2] = {};
 #pragma unroll
-  for (int ks = 0; ks < QW / 4; ++ks) {
-    double a[4], b[2];
+    for (int ks = 0; ks < QW / 4; ++ks) {
+      double a[4], b[2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) a[i] = Vs[32 * wm + 8 * i + g][4 * ks + c];
+      for (int i = 0; i < 4; ++i) a[i] = Vs[(32 * wm + 8 * i + g) * RU_LD + 4 * ks + c];
 #pragma unroll
-    for (int j = 0; j < 2; ++j) b[j] = Ws[16 * wn + 8 * j + g][4 * ks + c];
+      for (int j = 0; j < 2; ++j) b[j] = Wb[(16 * wn + 8 * j + g) * RU_LD + 4 * ks + c];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-  }
+        for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int r = r0 + 32 * wm + 8 * i + g;
-    if (r >= rows) continue;
+    for (int i = 0; i < 4; ++i) {
+      const int r = r0 + 32 * wm + 8 * i + g;
+      if (r >= rows) continue;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int col = c0 + 16 * wn + 8 * j + 2 * c;
-      double* dst = C + static_cast<int64_t>(r) * ldc + col;
-      const double2 o = make_double2(cf[i][j].x - acc[i][j][0], cf[i][j].y - acc[i][j][1]);
-      if (vec && col + 1 < nt) *reinterpret_cast<double2*>(dst) = o;
-      else {
-        if (col < nt) dst[0] = o.x;
-        if (col + 1 < nt) dst[1] = o.y;
+      for (int j = 0; j < 2; ++j) {
+        const int col = ct * RU + 16 * wn + 8 * j + 2 * c;
+        double* dst = C + static_cast<int64_t>(r) * ldc + col;
+        const double2 o = make_double2(cf[i][j].x - acc[i][j][0], cf[i][j].y - acc[i][j][1]);
+        if (vec && col + 1 < nt) *reinterpret_cast<double2*>(dst) = o;
+        else {
+          if (col < nt) dst[0] = o.x;
+          if (col + 1 < nt) dst[1] = o.y;
+        }
       }
     }
+    if (more) {
+      stage_tile(Ws + (buf ^ 1) * RU * RU_LD, wr);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) cf[i][j] = cfn[i][j];
+    }
+    __syncthreads();
+    buf ^= 1;
   }
 }
+
+bool g_ru_attr[64] = {};
 
 int launch_rank_update(double* C, int64_t ldc, const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t rows,
                        int64_t nt, int k, cudaStream_t st) {
   if (rows <= 0 || nt <= 0 || k <= 0) return NPW_OK;
-  dim3 grid(static_cast<unsigned>((nt + RU - 1) / RU), static_cast<unsigned>((rows + RU - 1) / RU));
-  rank_update_kernel<<<grid, 256, 0, st>>>(C, ldc, V, ldv, W, ldw, static_cast<int>(rows), static_cast<int>(nt), k,
-                                           aligned16(C, ldc) ? 1 : 0);
+  if (k > QW || !aligned16(W, ldw)) {
+    set_error("rank update: k = %d > 32 or unaligned W", k);
+    return NPW_ERR_UNSUPPORTED;
+  }
+  int dev = 0;
+  NPW_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 64 && !g_ru_attr[dev]) {
+    NPW_CUDA_CHECK(cudaFuncSetAttribute(rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM));
+    g_ru_attr[dev] = true;
+  }
+  const int64_t stripes = (rows + RU - 1) / RU, nct = (nt + RU - 1) / RU;
+  int64_t groups = (12 * 148 + stripes - 1) / stripes;      // enough CTAs for ~6 waves at 2 per SM
+  if (groups > nct) groups = nct;
+  if (groups < 1) groups = 1;
+  const int tiles_per_cta = static_cast<int>((nct + groups - 1) / groups);
+  dim3 grid(static_cast<unsigned>(stripes), static_cast<unsigned>((nct + tiles_per_cta - 1) / tiles_per_cta));
+  rank_update_kernel<<<grid, 256, RU_SMEM, st>>>(C, ldc, V, ldv, W, ldw, static_cast<int>(rows), static_cast<int>(nt), k,
+                                                 aligned16(C, ldc) ? 1 : 0, aligned16(V, ldv) ? 1 : 0, tiles_per_cta);
   NPW_LAUNCH_CHECK();
   return NPW_OK;
 }
@@ -610,56 +923,90 @@ int launch_rank_update(double* C, int64_t ldc, const double* V, int64_t ldv, con
 // Off-diagonal block column of T for the panel at j0 (w columns), dlarft's recurrence in block form:
 //   T[0:j0, j0:j0+w] = -T[0:j0, 0:j0] (G[0:j0, j0:j0+w] T_pp),   G = V^T V (upper part), T_pp = T[j0:j0+w, j0:j0+w].
 // CTA rb computes output rows [32 rb, 32 rb + 32): T is upper triangular, so only k-blocks kb >= rb contribute.
+// Four groups of 256 threads take the k-blocks kb = rb + grp, rb + grp + 4, ...; their sums are added in a fixed order.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) t_offdiag_kernel(double* __restrict__ T, int64_t ldt, const double* __restrict__ Gm,
-                                                        int64_t ldg, int j0, int w) {
-  __shared__ double sTpp[QW][QW + 1];
-  __shared__ double sG[QW][QW + 1];
-  __shared__ double sX[QW][QW + 1];     // G_blk T_pp
-  __shared__ double sTl[QW][QW + 1];    // T[32 rb.., 32 kb..]
+constexpr int TO_NG = 4;
+constexpr int TO_LD = QW + 4;                               // 36: conflict-free m8n8k4 fragment loads
+constexpr int TO_BLK = QW * TO_LD;
+constexpr int TO_SMEM = (1 + 3 * TO_NG) * TO_BLK * static_cast<int>(sizeof(double));
+
+// The 32 x 32 x 32 block products run on the fp64 tensor pipe: warp wi of a group owns the 8 x 16 output strip
+// (tile row wi / 2, tile columns 2 (wi % 2) and 2 (wi % 2) + 1) — 3 fragment loads per 2 DMMAs instead of 2 shared
+// loads per DFMA (round 2a: 16 us per trip, shared-memory bound).
+__global__ void __launch_bounds__(256 * TO_NG) t_offdiag_kernel(double* __restrict__ T, int64_t ldt, const double* __restrict__ Gm,
+                                                                int64_t ldg, int j0, int w) {
+  extern __shared__ __align__(16) double to_smem[];
+  double* sTpp = to_smem;                                   // [32][36]
+  const int grp = threadIdx.x >> 8;
+  const int t = threadIdx.x & 255;
+  double* sG = to_smem + TO_BLK * (1 + 3 * grp);            // G block, later this group's partial result
+  double* sX = sG + TO_BLK;                                 // G_blk T_pp
+  double* sTl = sX + TO_BLK;                                // T[32 rb.., 32 kb..]
   const int rb = blockIdx.x;
-  const int t = threadIdx.x;
-  const int ty = t >> 5, tx = t & 31;   // 8 x 32: thread owns rows ty, ty + 8, ty + 16, ty + 24 of column tx
-  for (int e = t; e < QW * QW; e += 256) {
+  const int wi = t >> 5, lane = t & 31;
+  const int g = lane >> 2, c = lane & 3;
+  const int tr = wi >> 1, tc0 = (wi & 1) * 2;
+  for (int e = threadIdx.x; e < QW * QW; e += 256 * TO_NG) {
     const int i = e >> 5, cc = e & 31;
-    sTpp[i][cc] = (i < w && cc < w) ? T[static_cast<int64_t>(j0 + i) * ldt + j0 + cc] : 0.0;
+    sTpp[i * TO_LD + cc] = (i < w && cc < w) ? T[static_cast<int64_t>(j0 + i) * ldt + j0 + cc] : 0.0;
   }
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  double acc[2][2] = {};
   const int nkb = (j0 + QW - 1) / QW;
-  for (int kb = rb; kb < nkb; ++kb) {
+  const int trips = (nkb - rb + TO_NG - 1) / TO_NG;         // same trip count for every group (barriers inside)
+  for (int it = 0; it < trips; ++it) {
+    const int kb = rb + grp + it * TO_NG;
     __syncthreads();
     for (int e = t; e < QW * QW; e += 256) {
       const int i = e >> 5, cc = e & 31;
       const int gr = kb * QW + i;
-      sG[i][cc] = (gr < j0 && cc < w) ? Gm[static_cast<int64_t>(gr) * ldg + j0 + cc] : 0.0;
-      const int tr = rb * QW + i, tc = kb * QW + cc;
-      sTl[i][cc] = (tr < j0 && tc < j0) ? T[static_cast<int64_t>(tr) * ldt + tc] : 0.0;
+      sG[i * TO_LD + cc] = (kb < nkb && gr < j0 && cc < w) ? Gm[static_cast<int64_t>(gr) * ldg + j0 + cc] : 0.0;
+      const int trw = rb * QW + i, tcl = kb * QW + cc;
+      sTl[i * TO_LD + cc] = (kb < nkb && trw < j0 && tcl < j0) ? T[static_cast<int64_t>(trw) * ldt + tcl] : 0.0;
+    }
+    __syncthreads();
+    double x[2][2] = {};
+#pragma unroll
+    for (int ks = 0; ks < QW / 4; ++ks) {
+      const double a = sG[(8 * tr + g) * TO_LD + 4 * ks + c];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) dmma884(x[u][0], x[u][1], a, sTpp[(4 * ks + c) * TO_LD + 8 * (tc0 + u) + g]);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      sX[(8 * tr + g) * TO_LD + 8 * (tc0 + u) + 2 * c] = x[u][0];
+      sX[(8 * tr + g) * TO_LD + 8 * (tc0 + u) + 2 * c + 1] = x[u][1];
     }
     __syncthreads();
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = ty + 8 * u;
-      double x = 0.0;
-#pragma unroll 8
-      for (int q = 0; q < QW; ++q) x = fma(sG[i][q], sTpp[q][tx], x);
-      sX[i][tx] = x;
-    }
-    __syncthreads();
+    for (int ks = 0; ks < QW / 4; ++ks) {
+      const double a = sTl[(8 * tr + g) * TO_LD + 4 * ks + c];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = ty + 8 * u;
-      double a = acc[u];
-#pragma unroll 8
-      for (int q = 0; q < QW; ++q) a = fma(sTl[i][q], sX[q][tx], a);
-      acc[u] = a;
+      for (int u = 0; u < 2; ++u) dmma884(acc[u][0], acc[u][1], a, sX[(4 * ks + c) * TO_LD + 8 * (tc0 + u) + g]);
     }
   }
+  __syncthreads();
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int r = rb * QW + ty + 8 * u;
-    if (r < j0 && tx < w) T[static_cast<int64_t>(r) * ldt + j0 + tx] = -acc[u];
+  for (int u = 0; u < 2; ++u) {
+    sG[(8 * tr + g) * TO_LD + 8 * (tc0 + u) + 2 * c] = acc[u][0];
+    sG[(8 * tr + g) * TO_LD + 8 * (tc0 + u) + 2 * c + 1] = acc[u][1];
+  }
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int i = 8 * tr + g, cc = 8 * (tc0 + u) + 2 * c + e;
+        double sum = 0.0;
+#pragma unroll
+        for (int q = 0; q < TO_NG; ++q) sum += to_smem[TO_BLK * (1 + 3 * q) + i * TO_LD + cc];
+        const int r = rb * QW + i;
+        if (r < j0 && cc < w) T[static_cast<int64_t>(r) * ldt + j0 + cc] = -sum;
+      }
   }
 }
+
+bool g_to_attr[64] = {};
 
 inline size_t align256(size_t x) { return (x + 255) & ~static_cast<size_t>(255); }
 
@@ -685,6 +1032,7 @@ QrWork qr_work_layout(int64_t m, int64_t n) {
 }
 
 int g_coop_grid[64] = {};
+bool g_qr_no_reg = false;
 
 }  // namespace
 }  // namespace npw
@@ -737,6 +1085,7 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
                                                                QR_SMEM_ROWS * QW * sizeof(double)));
     int g = sms * (per_sm > 0 ? 1 : 0);
     if (g > MAX_GRID) g = MAX_GRID;
+    if (const char* e = getenv("NPW_B200_QR_NO_REG")) g_qr_no_reg = atoi(e) != 0;   // tuning / test knob: shared-memory variant
     if (const char* e = getenv("NPW_B200_QR_GRID")) {       // tuning knob: CTAs of a panel launch
       const int v = atoi(e);
       if (v >= 1 && v < g) g = v;
@@ -775,7 +1124,9 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
     if (g < 1) g = 1;
     void* kargs[] = {&pa};
     const int64_t per = (rows + g - 1) / g;                 // rows per CTA, as the kernel computes it
-    if (per <= QR_SMEM_ROWS) {
+    if (per <= RWARPS * RPW && !g_qr_no_reg) {
+      NPW_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(qr_panel_reg_kernel), dim3(g), dim3(RTHREADS), kargs, 0, st));
+    } else if (per <= QR_SMEM_ROWS) {
       NPW_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(qr_panel_kernel<true>), dim3(g), dim3(QTHREADS), kargs,
                                                  static_cast<size_t>(per) * QW * sizeof(double), st));
     } else {
@@ -806,7 +1157,11 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
     if (rc) return rc;
     for (int64_t j0 = QW; j0 < n; j0 += QW) {
       const int w = static_cast<int>(n - j0 < QW ? n - j0 : QW);
-      t_offdiag_kernel<<<static_cast<unsigned>((j0 + QW - 1) / QW), 256, 0, st>>>(T, ldt, gram, n, static_cast<int>(j0), w);
+      if (dev < 64 && !g_to_attr[dev]) {
+        NPW_CUDA_CHECK(cudaFuncSetAttribute(t_offdiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TO_SMEM));
+        g_to_attr[dev] = true;
+      }
+      t_offdiag_kernel<<<static_cast<unsigned>((j0 + QW - 1) / QW), 256 * TO_NG, TO_SMEM, st>>>(T, ldt, gram, n, static_cast<int>(j0), w);
       NPW_LAUNCH_CHECK();
     }
   }
