@@ -821,6 +821,71 @@ def run_cholesky_arm(args):
 
 
 # ----------------------------------------------------------------------------------------------- TSQR workload (config 4)
+def golden_tsqr_parity(ctx, streams, name="tsqr_256_32"):
+    """The TSQR program on THIS process grid against the fixture written by the unmodified reference
+    (tests/golden/<name>.npz, oracle/make_golden.py): final R elementwise (same Householder convention, so signs agree)."""
+    from numpywren_b200.alg_wrappers import _place_by_row_block, tsqr
+    from numpywren_b200.matrix import BigMatrix
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    m, b, nlev = int(g["m"]), int(g["b"]), int(g["nlev"])
+    X = BigMatrix(f"bench_tsqr_golden_{os.getpid()}", shape=(m, b), shard_sizes=(b, b), device=ctx.device)
+    X.free()
+    _place_by_row_block(X, 0)
+    for j in range(m // b):
+        if ctx.is_mine(X, (j, 0)):
+            X.put_block(torch.from_numpy(np.ascontiguousarray(g["X"][j * b:(j + 1) * b])), j, 0)
+    program, meta = tsqr(X)
+    run_program(ctx, program, streams, consume=False)
+    Rs = meta["outputs"][0]
+    src = ctx.owner(Rs, (nlev, 0))
+    R = Rs._get_block_ref(nlev, 0).reshape(b, b).contiguous() if src == ctx.rank else torch.empty(b, b, dtype=torch.float64, device=ctx.device)
+    R = ctx.bcast_tile(R, src)
+    ref = torch.from_numpy(g["R"]).to(ctx.device)
+    err = float((R - ref).norm() / ref.norm())
+    free_all(X, *meta["outputs"])
+    return {"fixture": f"tests/golden/{name}.npz (written by the unmodified reference)", "rel_fro_R": err, "bar": PARITY_BAR,
+            "ok": bool(err <= PARITY_BAR), "leaves": m // b, "what": "final R of algs.TSQR on this process grid vs the reference's"}
+
+
+def golden_gemm_parity(ctx, streams, name="gemm_64_16"):
+    """The GEMM program on THIS process grid against the fixture written by the unmodified reference."""
+    from numpywren_b200 import alg_wrappers
+    from numpywren_b200.matrix import BigMatrix
+    path = os.path.join(ROOT, "tests", "golden", name + ".npz")
+    if not os.path.exists(path):
+        return None
+    g = np.load(path)
+    n, b = int(g["n"]), int(g["b"])
+    nb = n // b
+    mats = []
+    for tag in ("A", "B"):
+        M = BigMatrix(f"bench_gemm_golden_{tag}_{os.getpid()}", shape=(n, n), shard_sizes=(b, b), device=ctx.device)
+        M.free()
+        for i in range(nb):
+            for j in range(nb):
+                if ctx.is_mine(M, (i, j)):
+                    M.put_block(torch.from_numpy(np.ascontiguousarray(g[tag][i * b:(i + 1) * b, j * b:(j + 1) * b])), i, j)
+        mats.append(M)
+    program, meta = alg_wrappers.gemm_kloop(mats[0], mats[1], out_key=f"bench_gemm_golden_C_{os.getpid()}")
+    run_program(ctx, program, streams, consume=False)
+    C = meta["outputs"][0]
+    num = den = 0.0
+    for i in range(nb):
+        for j in range(nb):
+            src = ctx.owner(C, (i, j))
+            t = C._get_block_ref(i, j).reshape(b, b).contiguous() if src == ctx.rank else torch.empty(b, b, dtype=torch.float64, device=ctx.device)
+            t = ctx.bcast_tile(t, src)
+            ref = torch.from_numpy(np.ascontiguousarray(g["C"][i * b:(i + 1) * b, j * b:(j + 1) * b])).to(ctx.device)
+            num += float(((t - ref) ** 2).sum()); den += float((ref ** 2).sum())
+    free_all(*mats, *meta["outputs"], *meta.get("intermediates", []))
+    err = (num / den) ** 0.5
+    return {"fixture": f"tests/golden/{name}.npz (written by the unmodified reference)", "rel_fro_C": err, "bar": PARITY_BAR,
+            "ok": bool(err <= PARITY_BAR), "what": "C of the GEMM_ACC program on this process grid vs the reference's algs.GEMM result"}
+
+
 def run_tsqr_arm(args):
     """BASELINE config 4: TSQR m x 512 fp64, tile (65536, 512), binary reduction tree; row blocks sharded over the GPUs
     (block j on rank j mod world), tree merges exchange 2 MiB R factors over NVLink."""
@@ -887,6 +952,7 @@ def run_tsqr_arm(args):
     clocks = sampler.stop() if sampler is not None else None
     ms_per_step = float(np.mean(times))
     value = flops / (ms_per_step * 1e-3) * 1e-12
+    parity = golden_tsqr_parity(ctx, args.streams)
     roofline = None
     if ctx.rank == 0:
         peaks = measure_peaks(ctx.device)
@@ -918,7 +984,7 @@ def run_tsqr_arm(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args), "tile_tasks": nodes, "tree_levels": levels,
                            "placement": "row block j on rank j mod world", "streams": args.streams,
-                           "gram_residual_RtR_minus_XtX": err, "algorithmic_flops_per_step": flops,
+                           "gram_residual_RtR_minus_XtX": err, "parity_vs_golden": parity, "algorithmic_flops_per_step": flops,
                            "parity": "kernels vs LAPACK restatement at 1e-10 in tests/ (QR family: parity unpinned beyond LAPACK, DESIGN §7)",
                            "l2": "inputs larger than L2 (%.1f GB per step)" % (m * ncol * 8 / 1e9)},
                 "roofline": roofline, "cpu_baseline": None,
@@ -993,6 +1059,7 @@ def run_gemm_arm(args):
     ms_per_step = float(np.mean(times))
     value = flops / (ms_per_step * 1e-3) * 1e-12
     free_all(A, B)
+    parity = golden_gemm_parity(ctx, args.streams)
     roofline = tensor_roofline(ctx, b, value) if ctx.rank == 0 else None
     if ctx.rank == 0:
         grid = ctx.grid
@@ -1001,7 +1068,7 @@ def run_gemm_arm(args):
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args), "tile_tasks": nodes, "streams": args.streams,
                            "process_grid": (f"{grid.P}x{grid.Q} rotated block-cyclic over tile index" if grid else "1x1"),
-                           "tile_rel_err_vs_cublas_kloop": err, "algorithmic_flops_per_step": flops,
+                           "tile_rel_err_vs_cublas_kloop": err, "parity_vs_golden": parity, "algorithmic_flops_per_step": flops,
                            "l2": "inputs larger than L2 (%.1f GB of A and B tiles)" % (2 * n * n * 8 / 1e9)},
                 "roofline": roofline, "cpu_baseline": None,
                 "e2e": {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,

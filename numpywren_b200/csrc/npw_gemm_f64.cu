@@ -17,6 +17,8 @@
 //    k = 4c + 2h + e; A and B use the same slot->k permutation so the product is unchanged.
 //  * Grid = ceil(m/128) * ceil(n/128) CTAs, 1 CTA/SM (193 KB smem), rastered in 8-row groups
 //    so concurrently resident CTAs share operand panels in the 126 MB L2.
+#include <stdlib.h>
+
 #include "npw_common.cuh"
 
 namespace npw {
@@ -38,6 +40,16 @@ constexpr int STAGE_BYTES = STAGE_A + STAGE_B;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
 constexpr int RASTER_GROUP = 8;
 
+// tile-rows per raster group; NPW_B200_RASTER overrides the default (tuning knob, read once)
+inline int raster_group() {
+  static int v = [] {
+    const char* e = getenv("NPW_B200_RASTER");
+    const int x = e ? atoi(e) : RASTER_GROUP;
+    return x >= 1 && x <= 64 ? x : RASTER_GROUP;
+  }();
+  return v;
+}
+
 struct GemmArgs {
   double* C;
   const double* C0;
@@ -46,6 +58,7 @@ struct GemmArgs {
   double alpha, beta;
   int lower_only;
   int grid_m, grid_n;
+  int raster;          // tile-rows per raster group
   int vec_ok;
 };
 
@@ -62,10 +75,11 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   int tile_m, tile_n;
   {
     const int lin = blockIdx.x;
-    const int group_sz = RASTER_GROUP * p.grid_n;
+    const int RG = p.raster;
+    const int group_sz = RG * p.grid_n;
     const int gid = lin / group_sz;
-    const int first_m = gid * RASTER_GROUP;
-    const int gm = min(p.grid_m - first_m, RASTER_GROUP);
+    const int first_m = gid * RG;
+    const int gm = min(p.grid_m - first_m, RG);
     const int r = lin - gid * group_sz;
     tile_m = first_m + r % gm;
     tile_n = r / gm;
@@ -370,6 +384,7 @@ int launch_gemm(double* C, int64_t ldc, const double* C0, int64_t ldc0, const do
     p.alpha = alpha; p.beta = beta; p.lower_only = lower_only;
     p.grid_m = static_cast<int>((m + BM - 1) / BM);
     p.grid_n = static_cast<int>((n + BN - 1) / BN);
+    p.raster = raster_group();
     p.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && (ldc % 2 == 0) &&
                (C0 == nullptr || (((reinterpret_cast<uintptr_t>(C0) & 15u) == 0) && (ldc0 % 2 == 0)));
     gemm_nt_tma_kernel<<<p.grid_m * p.grid_n, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);

@@ -69,10 +69,10 @@ __device__ __forceinline__ void ll_store(uint64_t* slot, double v, uint32_t seq)
   const uint64_t tag = static_cast<uint64_t>(seq) << 32;
   const uint64_t w0 = (bits & 0xffffffffull) | tag;
   const uint64_t w1 = (bits >> 32) | tag;
-  asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
 }
 __device__ __forceinline__ void ll_load(const uint64_t* slot, uint64_t& w0, uint64_t& w1) {
-  asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
 }
 __device__ __forceinline__ bool ll_valid(uint64_t w0, uint64_t w1, uint32_t seq) {
   return static_cast<uint32_t>(w0 >> 32) == seq && static_cast<uint32_t>(w1 >> 32) == seq;
@@ -336,13 +336,17 @@ __global__ void __launch_bounds__(RTHREADS, 1) qr_panel_reg_kernel(PanelArgs p) 
   auto poll3 = [&](const uint64_t* s0, const uint64_t* s1, const uint64_t* s2, uint32_t seq, double& v0, double& v1, double& v2) {
     uint64_t a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0;
     const long long t0 = clock64();
-    bool ok = *static_cast<volatile int*>(p.err) != 0;
+    bool ok = false;
+    unsigned sweeps = 0;
     while (!ok) {
       if (s0) ll_load(s0, a0, a1);
       if (s1) ll_load(s1, b0, b1);
       if (s2) ll_load(s2, c0, c1);
       ok = (!s0 || ll_valid(a0, a1, seq)) && (!s1 || ll_valid(b0, b1, seq)) && (!s2 || ll_valid(c0, c1, seq));
-      if (!ok && clock64() - t0 > QR_SPIN_LIMIT) {
+      // every 1024 failed sweeps: give up if this or an earlier poll of the factorisation ran out of time (the error
+      // word is deliberately not read on the fast path: it would put an L2 round trip in front of every poll)
+      if (!ok && (++sweeps & 1023u) == 0 &&
+          (*static_cast<volatile int*>(p.err) != 0 || clock64() - t0 > QR_SPIN_LIMIT)) {
         *static_cast<volatile int*>(p.err) = 1;
         break;
       }
