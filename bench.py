@@ -923,10 +923,23 @@ def run_tsqr_arm(args):
             dist.all_reduce(G)
         return float((R.T @ R - G).norm() / G.norm())
 
-    def one(check=False):
+    timeline = [None]
+
+    def one(check=False, profile=False):
         X = make_input()
         program, meta = tsqr(X)
-        ms, launches, plan_s = run_program(ctx, program, args.streams, consume=False)
+        ms, launches, plan_s = run_program(ctx, program, args.streams, consume=False, profile=profile)
+        if profile:
+            from numpywren_b200 import job_runner
+            tl = [[name, int(v.get("j", -1)), int(v.get("level", -1)), round(s0, 2), round(e0, 2)]
+                  for name, v, s0, e0, _ in job_runner.node_timeline(program)]
+            out = [None] * ctx.world
+            if ctx.world > 1:
+                import torch.distributed as dist
+                dist.all_gather_object(out, tl)
+            else:
+                out = [tl]
+            timeline[0] = {"step_ms": ms, "per_rank_nodes": out, "columns": ["kernel", "j", "level", "start_ms", "end_ms"]}
         err = None
         if check:
             Rs = meta["outputs"][0]
@@ -952,6 +965,8 @@ def run_tsqr_arm(args):
     clocks = sampler.stop() if sampler is not None else None
     ms_per_step = float(np.mean(times))
     value = flops / (ms_per_step * 1e-3) * 1e-12
+    if args.trace:
+        one(profile=True)
     parity = golden_tsqr_parity(ctx, args.streams)
     roofline = None
     if ctx.rank == 0:
@@ -983,8 +998,9 @@ def run_tsqr_arm(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args), "tile_tasks": nodes, "tree_levels": levels,
-                           "placement": "row block j on rank j mod world", "streams": args.streams,
+                           "placement": "leaf j on rank j mod world; merge k of every tree level on rank k mod world", "streams": args.streams,
                            "gram_residual_RtR_minus_XtX": err, "parity_vs_golden": parity, "algorithmic_flops_per_step": flops,
+                           "node_timeline": timeline[0],
                            "parity": "kernels vs LAPACK restatement at 1e-10 in tests/ (QR family: parity unpinned beyond LAPACK, DESIGN §7)",
                            "l2": "inputs larger than L2 (%.1f GB per step)" % (m * ncol * 8 / 1e9)},
                 "roofline": roofline, "cpu_baseline": None,

@@ -32,6 +32,25 @@ def _place_by_row_block(mat, axis):
     mat.placement = placement
 
 
+def _place_tsqr_tree(mat):
+    """Placement of the TSQR trees (tiles indexed (level, j), j a multiple of 2**level): node k = j / 2**level of its level
+    lives on rank k mod world.  Leaves (level 0) stay with their row block (rank j mod world); the merges of every level
+    are dealt round-robin over ALL ranks instead of piling up on the ranks that hold the even row blocks (with the plain
+    row-block map every merge of a 2-GPU run — and every merge above level 3 of an 8-GPU run — lands on rank 0).  The
+    price is one extra 2 MiB R tile over NVLink per merge."""
+    from . import parallel
+
+    def placement(true_idx):
+        grid = parallel.current_grid()
+        level, j = int(true_idx[0]), int(true_idx[1])
+        k = j >> level
+        if grid is None:
+            return k, 0
+        r = k % grid.world
+        return r // grid.Q, r % grid.Q
+    mat.placement = placement
+
+
 def cholesky(X, truncate=0):
     """Tiled Cholesky of the SPD BigMatrix ``X`` → lower factor ``O`` (unwritten upper tiles read as zeros)."""
     b = X.shard_sizes[0]
@@ -63,13 +82,13 @@ def tsqr(X, truncate=0):
     V_sharded = BigMatrix("tsqr_V({0})".format(X.key), shape=(num_tree_levels * shard_size * b_fac, X.shape[0]),
                           shard_sizes=(shard_size * b_fac, shard_size), bucket=X.bucket, write_header=True, safe=False,
                           device=X.device)
-    # multi-GPU placement: everything derived from row block j lives on rank j mod world (leaves are embarrassingly
-    # parallel, only the R factors of the reduction tree cross GPUs); tile shapes are declared because these matrices
-    # are allocated with the reference's loose shapes (safe=False, alg_wrappers.py:36-38)
+    # multi-GPU placement: leaf j lives on rank j mod world (leaves are embarrassingly parallel), the merges of every tree
+    # level are dealt round-robin over the ranks (_place_tsqr_tree); only 2 MiB R factors cross GPUs.  Tile shapes are
+    # declared because these matrices are allocated with the reference's loose shapes (safe=False, alg_wrappers.py:36-38)
     n = X.shape[1]
     _place_by_row_block(X, axis=0)
     for mat in (R_sharded, T_sharded, V_sharded):
-        _place_by_row_block(mat, axis=1)
+        _place_tsqr_tree(mat)
     R_sharded.tile_shape = lambda idx: (n, n)
     T_sharded.tile_shape = lambda idx: (n, n)
     V_sharded.tile_shape = lambda idx: (X.block_shape(idx[1], 0)[0], n) if idx[0] == 0 else (2 * n, n)
