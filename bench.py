@@ -1024,6 +1024,8 @@ def run_gemm_arm(args):
     flops = 2.0 * n ** 3
     A = BigMatrix("bench_gemm_A", shape=(n, n), shard_sizes=(b, b), device=ctx.device); A.free()
     B = BigMatrix("bench_gemm_B", shape=(n, n), shard_sizes=(b, b), device=ctx.device); B.free()
+    alg_wrappers.place_plain_block_cyclic(A)       # before the tiles are created: ownership decides where they live
+    alg_wrappers.place_plain_block_cyclic(B)
     for i in range(nb):
         for k in range(nb):
             for mtx, seed in ((A, 1), (B, 2)):
@@ -1083,7 +1085,7 @@ def run_gemm_arm(args):
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(args), "tile_tasks": nodes, "streams": args.streams,
-                           "process_grid": (f"{grid.P}x{grid.Q} rotated block-cyclic over tile index" if grid else "1x1"),
+                           "process_grid": (f"{grid.P}x{grid.Q} plain block-cyclic over tile index" if grid else "1x1"),
                            "tile_rel_err_vs_cublas_kloop": err, "parity_vs_golden": parity, "algorithmic_flops_per_step": flops,
                            "l2": "inputs larger than L2 (%.1f GB of A and B tiles)" % (2 * n * n * 8 / 1e9)},
                 "roofline": roofline, "cpu_baseline": None,

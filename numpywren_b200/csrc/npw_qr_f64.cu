@@ -282,7 +282,11 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(PanelArgs p) {
 constexpr int RTHREADS = 256, RWARPS = 8, RPW = 56;
 constexpr int RPIV = QW / RWARPS + 1;   // register rows of a warp that can be (or sit directly below) a pivot row of the launch
 
-__global__ void __launch_bounds__(RTHREADS, 1) qr_panel_reg_kernel(PanelArgs p) {
+// 224 registers x 256 threads leave 8192 of the SM's 65536 registers free ON PURPOSE: the kernel spins on packets from its
+// sibling CTAs, so every one of them must become resident — also on an SM where a tiny kernel that itself waits for
+// another GPU (the tile exchange's wait_signal) is parked.  With the full 255 registers such an SM could never take its
+// CTA, and the 8-GPU TSQR deadlocked until the exchange's signal timeout (profiles/r02i_*).
+__global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
   const int G = gridDim.x;
   const int cta = blockIdx.x;
   const int lane = threadIdx.x & 31;

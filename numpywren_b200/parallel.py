@@ -298,7 +298,7 @@ class SymmTileExchange(TileExchange):
     Signals are per (src, dst) binary semaphores consumed in plan order, so the k-th wait pairs with the k-th copy.
     """
 
-    SIGNAL_TIMEOUT_MS = 120000
+    SIGNAL_TIMEOUT_MS = int(os.environ.get("NPW_B200_SIGNAL_TIMEOUT_MS", "120000"))
 
     def __init__(self, compiled, grid: ProcessGrid, device):
         super().__init__(compiled, grid)
