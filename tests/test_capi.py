@@ -97,3 +97,20 @@ def test_flop_models_match_reference_formulas():
     assert kernels.gemm.flops(torch.zeros(3, 4), torch.zeros(4, 5)) == 2 * 3 * 4 * 5
     assert kernels.trsm.flops(torch.zeros(4, 4), torch.zeros(7, 4)) == 4 * 4 * 4
     assert kernels.qr_factor.flops(torch.zeros(10, 4), torch.zeros(6, 4)) == 2 * 16 * 16 - 2 * 64 / 3
+
+
+def test_spinning_panel_kernel_leaves_register_headroom():
+    """qr_panel_reg_kernel spins on packets from its sibling CTAs, so every CTA must become resident — also on an SM where a
+    tiny kernel that waits for another GPU is parked (the tile exchange's wait_signal).  With 255 registers x 256 threads it
+    filled the register file and the 8-GPU TSQR deadlocked (profiles/r02i_call13_failures.txt): keep >= 4096 registers free."""
+    import re
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    lib_path = os.path.join(ROOT, "numpywren_b200", "lib", "libnpw_b200.so")
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", lib_path], capture_output=True, text=True).stdout
+    m = re.search(r"Function [^\n]*qr_panel_reg_kernel[^\n]*:\s*\n\s*REG:(\d+)", out)
+    assert m, "qr_panel_reg_kernel not found in the library"
+    regs = int(m.group(1))
+    assert regs * 256 <= 65536 - 4096, regs

@@ -96,3 +96,56 @@ def test_grid_shapes_and_ownership():
     assert max(work) / (sum(work) / 8) < 1.03
     with pytest.raises(ValueError):
         parallel.ProcessGrid(8, 0, shape=(3, 3))
+
+
+def test_tsqr_merges_are_dealt_over_all_ranks():
+    """alg_wrappers._place_tsqr_tree: leaf j on rank j mod world, merge k of every level on rank k mod world (with the plain
+    row-block map every merge of a 2-rank run landed on rank 0: profiles/r02h timeline)."""
+    from numpywren_b200 import alg_wrappers
+    from numpywren_b200.matrix import BigMatrix
+    for world in (2, 4, 8):
+        grid = parallel.ProcessGrid(world, 0)
+        parallel.set_grid(grid)
+        try:
+            X = BigMatrix(f"place_tsqr_{world}", shape=(64 * 8, 8), shard_sizes=(8, 8), device="cpu")
+            program, meta = alg_wrappers.tsqr(X)
+            plan = parallel.TransferPlan(program.program, grid)
+            per_level = {}
+            for n in program.program.nodes:
+                lvl = int(n.var_values.get("level", -1)) + 1
+                per_level.setdefault(lvl, [0] * world)[plan.exec_rank[n.nid]] += 1
+            assert per_level[0] == [64 // world] * world                      # leaves
+            for lvl, counts in per_level.items():
+                total = sum(counts)
+                assert max(counts) <= -(-total // world), (world, lvl, counts)   # ceil(total / world): round-robin
+            # all three outputs of a node share an owner (the engine runs a node where its first output lives)
+            for n in program.program.nodes:
+                assert len({grid.owner(m, idx) for (m, idx) in n.writes}) == 1
+        finally:
+            parallel.set_grid(None)
+
+
+def test_gemm_plain_block_cyclic_halves_the_inbox():
+    """alg_wrappers.place_plain_block_cyclic: GEMM_ACC on a 2x4 grid needs 128 remote tiles per rank with the plain map,
+    256 with the rotated (Cholesky) map — 64 GB instead of 131 GB of inbox at N=131072 / tile 8192."""
+    from numpywren_b200 import alg_wrappers
+    from numpywren_b200.matrix import BigMatrix
+    grid = parallel.ProcessGrid(8, 0)
+    parallel.set_grid(grid)
+    try:
+        nb = 16
+        A = BigMatrix("plain_gemm_A", shape=(nb * 4, nb * 4), shard_sizes=(4, 4), device="cpu")
+        B = BigMatrix("plain_gemm_B", shape=(nb * 4, nb * 4), shard_sizes=(4, 4), device="cpu")
+        alg_wrappers.place_plain_block_cyclic(A)
+        alg_wrappers.place_plain_block_cyclic(B)
+        program, meta = alg_wrappers.gemm_kloop(A, B, out_key="plain_gemm_C")
+        plan = parallel.TransferPlan(program.program, grid)
+        _, _, max_slots = plan.assign_inbox_slots()
+        assert max_slots == 128
+        C = meta["outputs"][0]
+        owners = [[grid.owner(C, (i, j)) for j in range(nb)] for i in range(nb)]
+        assert all(owners[i][j] == (i % 2) * 4 + (j % 4) for i in range(nb) for j in range(nb))
+        counts = [sum(row.count(r) for row in owners) for r in range(8)]
+        assert counts == [nb * nb // 8] * 8
+    finally:
+        parallel.set_grid(None)

@@ -255,6 +255,17 @@ def test_qr_factor_matches_oracle(cuda_device, m, n):
     assert np.linalg.norm(q[:, :n] @ Rn - a) / np.linalg.norm(a) < 1e-13
 
 
+@pytest.mark.parametrize("m,n", [(70000, 64), (120000, 32), (66000, 40)])
+def test_qr_factor_tall_tiles_use_the_other_panel_variants(cuda_device, m, n):
+    """More than 448 rows per CTA (m > 66304 on 148 SMs) takes the shared-memory panel kernel, more than 672 the global
+    one; 66000 rows is the register-resident kernel at the edge of its capacity.  Same V, T, R as LAPACK in all three."""
+    a = np.random.RandomState(m % 1000 + n).randn(m, n)
+    V, T, R = kernels.qr_factor(dev(a, cuda_device))
+    v, t, r = orc.qr_factor(a)
+    assert rel(R, r) < TOL and rel(V, v) < TOL and rel(T, t) < TOL
+    assert not bool(torch.isnan(T).any())
+
+
 def test_qr_factor_stacks_blocks_like_tsqr_merge(cuda_device):
     """TSQR merge node: qr_factor(R_left, R_right) on two upper-triangular factors (algs.py:36)."""
     rs = np.random.RandomState(12)
