@@ -182,7 +182,8 @@ int npw_tpqrt_f64(double* V2, int64_t ldv, double* T, int64_t ldt,
                   int64_t n, void* work, npw_stream_t stream);
 
 /* ------------------------------------------------------------------------
- * EXPERIMENTAL (never run on hardware in round 1; not used by the default path):
+ * OPTIONAL, off by default (the engine uses it only with NPW_B200_SYRK=i8emu; ran and
+ * passed parity on B200 in round 2, tests/test_i8emu_gpu.py):
  * kernels.syrk (kernels.py:212-215) with the product X Y^T emulated on the int8
  * tensor cores (tcgen05.mma kind::i8) — DESIGN.md §8, tools/ozaki_prototype.py.
  *   npw_split_i8_f64: X (rows x k, fp64) -> `ndigits` signed int8 digit planes

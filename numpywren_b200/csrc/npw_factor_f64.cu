@@ -16,6 +16,10 @@
 //         solves its 64 rows of A_[j+1:, j] against it      leaf (<= 128 cols): panel_kernel, no factorisation
 //         block column's other columns -= W W^T  (k = 128)
 //       trailing matrix -= P P^T  (k = 512, lower CTAs)
+#include <stdlib.h>
+
+#include <mutex>
+
 #include "npw_common.cuh"
 
 namespace npw {
@@ -451,7 +455,8 @@ int launch_panel(const double* Ajj, int64_t lda, int nbk, double* Ldiag, double*
   int rc = set_factor_attrs();
   if (rc) return rc;
   // 64-row chunks (4-row register tiles) spread a tile's panel over ~64 SMs; tall panels use 128-row chunks
-  const bool small = rest <= 64 * 192;
+  static const int64_t small_rows = [] { const char* e = getenv("NPW_B200_PANEL_SMALL_ROWS"); return e ? atoll(e) : 64ll * 192; }();
+  const bool small = rest <= small_rows;
   const int per = small ? NT * 4 : NT * 8;
   const unsigned grid = static_cast<unsigned>((rest + per - 1) / per + (do_factor ? 1 : 0));
   if (grid == 0) return NPW_OK;
@@ -496,6 +501,42 @@ int trsm_rec(double* Bo, int64_t ldbo, const double* L, int64_t ldl, int64_t m, 
                    -1.0, 1.0, 0, st);
   if (rc) return rc;
   return trsm_rec(Bo, ldbo, L, ldl, m, j0 + n1, n2, st);
+}
+
+// ---- fork / join helper: the rows of B are independent problems, so a large solve is cut into two row halves that run
+// on two streams — the latency-bound 128-column leaves of one half overlap the GEMM updates of the other (alone on a
+// GPU, which is how the panel solves of the multi-GPU Cholesky mostly run, the one-stream solve left ~40 % of the SMs'
+// time unused).  A few side streams per device, used round-robin; the mutex only covers the enqueue sequence.
+struct ForkJoin {
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  std::mutex mu;
+};
+constexpr int FJ_SLOTS = 2, FJ_LEVELS = 8;
+ForkJoin g_fj[16][FJ_LEVELS][FJ_SLOTS];
+std::atomic<unsigned> g_fj_next{0};
+
+// the side stream gets the priority of the calling stream: the second half must neither overtake nor lag behind the
+// work the engine ordered by priority
+ForkJoin* acquire_fork_join(cudaStream_t st) {
+  int dev = 0, lo = 0, hi = 0, prio = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 16) return nullptr;
+  if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess || cudaStreamGetPriority(st, &prio) != cudaSuccess) return nullptr;
+  int level = prio - hi;                                  // 0 = greatest priority
+  if (level < 0) level = 0;
+  if (level >= FJ_LEVELS) level = FJ_LEVELS - 1;
+  ForkJoin* fj = &g_fj[dev][level][g_fj_next.fetch_add(1, std::memory_order_relaxed) % FJ_SLOTS];
+  fj->mu.lock();
+  if (!fj->side) {
+    if (cudaStreamCreateWithPriority(&fj->side, cudaStreamNonBlocking, prio) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fj->fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&fj->join, cudaEventDisableTiming) != cudaSuccess) {
+      fj->side = nullptr;
+      fj->mu.unlock();
+      return nullptr;
+    }
+  }
+  return fj;
 }
 
 }  // namespace
@@ -548,6 +589,28 @@ int npw_trsm_rlt_f64(double* B_out, int64_t ldbo, const double* L, int64_t ldl, 
   if (B_out != B) {
     int rc = npw::launch_copy2d(B_out, ldbo, B, ldb, m, n, 0, st);
     if (rc) return rc;
+  }
+  // two row halves on two streams when both halves still fill the GPU's GEMM grid (see ForkJoin)
+  static const bool split_ok = [] { const char* e = getenv("NPW_B200_TRSM_SPLIT"); return !e || atoi(e) != 0; }();
+  if (split_ok && m >= 2048 && n >= 1024) {
+    if (npw::ForkJoin* fj = npw::acquire_fork_join(st)) {
+      const int64_t h = ((m / 2 + npw::NB - 1) / npw::NB) * npw::NB;
+      int rc = NPW_OK, rc2 = NPW_OK;
+      cudaError_t e = cudaEventRecord(fj->fork, st);
+      if (e == cudaSuccess) e = cudaStreamWaitEvent(fj->side, fj->fork, 0);
+      if (e == cudaSuccess) {
+        rc = npw::trsm_rec(B_out, ldbo, L, ldl, h, 0, n, st);
+        rc2 = npw::trsm_rec(B_out + h * ldbo, ldbo, L, ldl, m - h, 0, n, fj->side);
+        e = cudaEventRecord(fj->join, fj->side);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(st, fj->join, 0);
+      }
+      fj->mu.unlock();
+      if (e != cudaSuccess) {
+        npw::set_error("trsm fork/join: %s", cudaGetErrorString(e));
+        return NPW_ERR_CUDA;
+      }
+      return rc ? rc : rc2;
+    }
   }
   return npw::trsm_rec(B_out, ldbo, L, ldl, m, 0, n, st);
 }

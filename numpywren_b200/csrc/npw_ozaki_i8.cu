@@ -1,9 +1,10 @@
-// npw_ozaki_i8.cu — EXPERIMENTAL: fp64 syrk emulated on the int8 tensor cores (tcgen05.mma kind::i8), DESIGN.md §8.
+// npw_ozaki_i8.cu — fp64 syrk emulated on the int8 tensor cores (tcgen05.mma kind::i8), DESIGN.md §8.
 //
-// STATUS: written and cross-compiled in round 1 AFTER the GPU budget was spent — it has never run on a B200.  Nothing
-// in the default path calls it: the engine uses it only with NPW_B200_SYRK=i8emu, and its tests carry the
-// `gpu_experimental` marker, which the round-end `-m gpu` run does not select.  The numerics it implements are the
-// ones validated on the CPU in tools/ozaki_prototype.py (tests/test_ozaki_prototype.py).
+// STATUS: optional path, OFF by default (the engine uses it only with NPW_B200_SYRK=i8emu; bench.py then labels the
+// line's dtype "f64 emulated on int8 tensor cores").  First ran on a B200 in round 2: descriptor probe, digit extraction
+// and products bit-for-bit against the CPU prototype (tools/ozaki_prototype.py), 4096^3 in 2.1 / 2.6 / 3.1 ms with
+// 6 / 7 / 8 digits against 3.83 ms native (profiles/r02c_syrk_i8emu_timing.jsonl), tensor pipe 30 % active
+// (profiles/r02c_ozaki_syrk_i8_kernel_ncu.json).  Tests: tests/test_i8emu_gpu.py (incl. a whole Cholesky vs the oracle).
 //
 // Replaces (optionally) the arithmetic of kernels.syrk (reference kernels.py:212-215, C = S - X Y^T) by
 //   1. npw_split_i8_f64 : every row of X (m x k fp64) is scaled by 2^-e_i (e_i = exponent of the row's largest entry)

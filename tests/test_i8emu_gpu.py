@@ -1,9 +1,7 @@
-"""EXPERIMENTAL kernels (csrc/npw_ozaki_i8.cu): fp64 syrk emulated on the int8 tensor cores.  Written after round 1's GPU
-budget was spent, so these tests have never run; they carry their own marker and are NOT selected by `-m gpu`:
-
-    NPW_B200_EXPERIMENTAL=1 timeout 300 python -m pytest tests/test_i8emu_experimental.py -m gpu_experimental -x -q
-
-Order matters when debugging: digits first (plain CUDA), then one 128 x 64 x 128 tile, then the benchmark tile."""
+"""fp64 syrk emulated on the int8 tensor cores (csrc/npw_ozaki_i8.cu, tcgen05.mma kind::i8): digit extraction and the
+product kernel against the CPU prototype of the same arithmetic (tools/ozaki_prototype.py), and a whole Cholesky with the
+emulated syrk against the oracle at the parity bar.  First ran on a B200 in round 2 (profiles/r02a_tcgen05_i8_probe.log,
+r02c_syrk_i8emu_timing.jsonl); the engine uses the kernel only with NPW_B200_SYRK=i8emu."""
 import os
 import sys
 
@@ -16,9 +14,7 @@ from numpywren_b200 import kernels
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
 import ozaki_prototype as oz  # noqa: E402
 
-pytestmark = [pytest.mark.gpu_experimental,
-              pytest.mark.skipif(os.environ.get("NPW_B200_EXPERIMENTAL") != "1",
-                                 reason="never-run tcgen05 kernels: set NPW_B200_EXPERIMENTAL=1 (and wrap the run in `timeout`)")]
+pytestmark = pytest.mark.gpu
 
 
 def dev(a, device):
@@ -67,3 +63,35 @@ def test_syrk_i8emu_in_place_and_lower_only(cuda_device):
     # 6 digits: 4.7e-12 of |x_i||y_j| per entry (profiles/r02b_syrk_i8emu_timing.jsonl), |x_i|^2 ~ k = 256
     assert np.abs(c[low] - exact[low]).max() < 1e-10 * 256
     assert np.array_equal(c[~low], s[~low])                  # the others are left alone
+
+
+@pytest.mark.parametrize("digits", [7, 8])
+def test_cholesky_with_emulated_syrk_against_oracle(unique_key, cuda_device, monkeypatch, digits):
+    """N=2048 with 256-tiles, every syrk product on the int8 tensor cores (trsm / potrf native fp64): the factor still
+    matches the oracle's at the 1e-10 parity bar (7 digits = 48 mantissa bits per row-scaled entry, 8 digits = 55)."""
+    from numpywren_b200 import job_runner
+    from numpywren_b200 import lambdapack as lp
+    from numpywren_b200.alg_wrappers import cholesky
+    from numpywren_b200.matrix import BigMatrix
+    from oracle import npw_oracle as orc
+    monkeypatch.setenv("NPW_B200_SYRK", "i8emu")
+    monkeypatch.setenv("NPW_B200_I8_DIGITS", str(digits))
+    n, b = 2048, 256
+    nb = n // b
+    A = BigMatrix(unique_key(f"i8chol{digits}"), shape=(n, n), shard_sizes=(b, b))
+    I = orc.OracleBigMatrix("I", (n, n), (b, b))
+    for j in range(nb):
+        for k in range(nb):
+            t = orc.spd_tile(j, k, b, n, width=64)
+            I.put_block(t, j, k)
+            A.put_block(t, j, k)
+    O_ref, _ = orc.run_cholesky(I)
+    program, meta = cholesky(A)
+    before = kernels._capi.launch_count()
+    program.start()
+    job_runner.lambdapack_run(program, timeout=120)
+    assert program.program_status() == lp.PS.SUCCESS
+    assert program._engine.syrk_mode == "i8emu"
+    L, Lref = meta["outputs"][0].numpy(), O_ref.numpy()
+    assert np.linalg.norm(L - Lref) / np.linalg.norm(Lref) < 1e-10
+    assert kernels._capi.launch_count() > before
