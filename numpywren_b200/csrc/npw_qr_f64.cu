@@ -527,7 +527,8 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
 // prefetched into registers while the current one feeds the DMMAs.  8 warps, warp tile 16 x 16 (2 x 2 DMMA tiles).
 // tn_partial_kernel (generic): plain DFMA, any alignment.
 // ------------------------------------------------------------------------------------------------
-constexpr int TDM = 64, TDN = 32, TDK = 32;
+constexpr int TDM = 64, TDN = 32, TDK = 32;   // measured: 64-row chunks at 2 CTAs/SM 17 % slower, 16-row chunks at 4 CTAs/SM 5 % slower
+constexpr int TD_UA = TDK * (TDM / 2) / 256, TD_UB = TDK * (TDN / 2) / 256;   // double2 per thread and chunk
 constexpr int TD_LDA = TDM + 4, TD_LDB = TDN + 4;
 constexpr int TD_SMEM = 2 * TDK * (TD_LDA + TD_LDB) * static_cast<int>(sizeof(double));   // 53248 B
 
@@ -544,11 +545,11 @@ __global__ void __launch_bounds__(256, 3) tn_dmma_kernel(double* __restrict__ P,
   const int warp = t >> 5, lane = t & 31;
   const int g = lane >> 2, c = lane & 3;
   const int wm = warp >> 1, wn = warp & 1;                  // warp tile: rows 16 wm.., cols 16 wn..
-  // staging assignment: A chunk = 32 rows x 32 double2 -> 4 per thread; B chunk = 32 rows x 16 double2 -> 2 per thread
-  double2 ra[4], rb[2];
+  // staging assignment: A chunk = TDK rows x 32 double2, B chunk = TDK rows x 16 double2
+  double2 ra[TD_UA], rb[TD_UB];
   auto fetch = [&](int kb) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < TD_UA; ++u) {
       const int e = t + 256 * u;
       const int r = kb + (e >> 5), col = tm + 2 * (e & 31);
       double2 v = make_double2(0.0, 0.0);
@@ -560,7 +561,7 @@ __global__ void __launch_bounds__(256, 3) tn_dmma_kernel(double* __restrict__ P,
       ra[u] = v;
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < TD_UB; ++u) {
       const int e = t + 256 * u;
       const int r = kb + (e >> 4), col = tn + 2 * (e & 15);
       double2 v = make_double2(0.0, 0.0);
@@ -574,12 +575,12 @@ __global__ void __launch_bounds__(256, 3) tn_dmma_kernel(double* __restrict__ P,
   };
   auto stage = [&](int buf) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < TD_UA; ++u) {
       const int e = t + 256 * u;
       *reinterpret_cast<double2*>(As + (buf * TDK + (e >> 5)) * TD_LDA + 2 * (e & 31)) = ra[u];
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < TD_UB; ++u) {
       const int e = t + 256 * u;
       *reinterpret_cast<double2*>(Bs + (buf * TDK + (e >> 4)) * TD_LDB + 2 * (e & 15)) = rb[u];
     }
@@ -775,36 +776,38 @@ int launch_tn(double* C, int64_t ldc, const double* A, int64_t lda, const double
 // is read and written exactly once and gets 2 x 32 flop: HBM-bound (the tensor pipe would sustain ~1.4x the traffic).
 // The C fragments are requested before the operands are staged so that the loads overlap the staging and the math.
 // ------------------------------------------------------------------------------------------------
-constexpr int RU = 64, RU_LD = QW + 4;
-constexpr int RU_SMEM = 3 * RU * RU_LD * static_cast<int>(sizeof(double));   // V tile + double-buffered W tile
+constexpr int RU = 64, RU_N = 32, RU_LD = QW + 4;        // 64-row stripe, 32-column tiles
+constexpr int RU_SMEM = (RU + 2 * RU_N) * RU_LD * static_cast<int>(sizeof(double));   // V tile + double-buffered W tile = 36 KB
 
-// A CTA owns a 64-row stripe of C and walks over `tiles_per_cta` column tiles of 64: the V tile is staged once, the W
+// A CTA owns a 64-row stripe of C and walks over `tiles_per_cta` column tiles of 32: the V tile is staged once, the W
 // tile of the next column tile and the next C fragments are requested before the current tile is multiplied, so the
-// HBM stream never waits for the math.
-__global__ void __launch_bounds__(256, 2) rank_update_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ V,
+// HBM stream never waits for the math.  The kernel is memory-bound (the DMMAs of a tile take a third of the time its
+// 32 KB of C traffic needs at HBM speed), so it is built for bytes in flight: small register tiles (warp tile 16 x 16),
+// ~80 registers, three CTAs per SM, each with the loads of two tiles outstanding.
+__global__ void __launch_bounds__(256, 3) rank_update_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ V,
                                                              int64_t ldv, const double* __restrict__ W, int64_t ldw, int rows, int nt,
                                                              int k, int vec, int vecv, int tiles_per_cta) {
   extern __shared__ __align__(16) double ru_smem[];
   double* Vs = ru_smem;                                     // [RU][RU_LD]
-  double* Ws = ru_smem + RU * RU_LD;                        // [2][RU][RU_LD]
+  double* Ws = ru_smem + RU * RU_LD;                        // [2][RU_N][RU_LD]
   const int r0 = blockIdx.x * RU;
-  const int nct = (nt + RU - 1) / RU;
+  const int nct = (nt + RU_N - 1) / RU_N;
   const int ct0 = blockIdx.y * tiles_per_cta;
   const int ct1 = min(nct, ct0 + tiles_per_cta);
   if (ct0 >= ct1) return;
   const int t = threadIdx.x;
   const int warp = t >> 5, lane = t & 31;
   const int g = lane >> 2, c = lane & 3;
-  const int wm = warp >> 2, wn = warp & 3;                  // warp tile: rows 32 wm.., cols 16 wn..
+  const int wm = warp >> 1, wn = warp & 1;                  // warp tile: rows 16 wm.., cols 16 wn..
 
-  // this lane's C fragments of column tile ct: rows r0 + 32 wm + 8 i + g, cols 64 ct + 16 wn + 8 j + 2 c + {0, 1}
-  auto load_c = [&](int ct, double2 (&cf)[4][2]) {
+  // this lane's C fragments of column tile ct: rows r0 + 16 wm + 8 i + g, cols 32 ct + 16 wn + 8 j + 2 c + {0, 1}
+  auto load_c = [&](int ct, double2 (&cf)[2][2]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + 32 * wm + 8 * i + g;
+    for (int i = 0; i < 2; ++i) {
+      const int r = r0 + 16 * wm + 8 * i + g;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int col = ct * RU + 16 * wn + 8 * j + 2 * c;
+        const int col = ct * RU_N + 16 * wn + 8 * j + 2 * c;
         double2 v = make_double2(0.0, 0.0);
         if (r < rows) {
           const double* src = C + static_cast<int64_t>(r) * ldc + col;
@@ -818,67 +821,60 @@ __global__ void __launch_bounds__(256, 2) rank_update_kernel(double* __restrict_
       }
     }
   };
-  // a 64 x 32 operand tile (row stride ld) as 4 double2 per thread
-  auto fetch_tile = [&](const double* M, int64_t ld, int row0, int nrows, int aligned, double2 (&wr)[4]) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = t + 256 * u;
-      const int rr = row0 + (e >> 4), q = 2 * (e & 15);
-      double2 v = make_double2(0.0, 0.0);
-      if (rr < nrows) {
-        const double* src = M + static_cast<int64_t>(rr) * ld + q;
-        if (aligned && q + 1 < k) v = *reinterpret_cast<const double2*>(src);
-        else {
-          if (q < k) v.x = src[0];
-          if (q + 1 < k) v.y = src[1];
-        }
+  // an NR x 32 operand tile (row stride ld) as NR / 16 double2 per thread
+  auto fetch_one = [&](const double* M, int64_t ld, int row0, int nrows, int aligned, int e) -> double2 {
+    const int rr = row0 + (e >> 4), q = 2 * (e & 15);
+    double2 v = make_double2(0.0, 0.0);
+    if (rr < nrows) {
+      const double* src = M + static_cast<int64_t>(rr) * ld + q;
+      if (aligned && q + 1 < k) v = *reinterpret_cast<const double2*>(src);
+      else {
+        if (q < k) v.x = src[0];
+        if (q + 1 < k) v.y = src[1];
       }
-      wr[u] = v;
     }
+    return v;
   };
-  auto stage_tile = [&](double* dst, const double2 (&wr)[4]) {
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int e = t + 256 * u;
-      *reinterpret_cast<double2*>(dst + (e >> 4) * RU_LD + 2 * (e & 15)) = wr[u];
-    }
+  auto stage_one = [&](double* dst, int e, double2 v) {
+    *reinterpret_cast<double2*>(dst + (e >> 4) * RU_LD + 2 * (e & 15)) = v;
   };
 
-  double2 cf[4][2], cfn[4][2], wr[4];
+  double2 cf[2][2], cfn[2][2], wr[2];
   load_c(ct0, cf);
-  fetch_tile(V, ldv, r0, rows, vecv, wr);
-  stage_tile(Vs, wr);
-  fetch_tile(W, ldw, ct0 * RU, nt, 1, wr);
-  stage_tile(Ws, wr);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) stage_one(Vs, t + 256 * u, fetch_one(V, ldv, r0, rows, vecv, t + 256 * u));
+#pragma unroll
+  for (int u = 0; u < 2; ++u) stage_one(Ws, t + 256 * u, fetch_one(W, ldw, ct0 * RU_N, nt, 1, t + 256 * u));
   __syncthreads();
   int buf = 0;
   for (int ct = ct0; ct < ct1; ++ct) {
     const bool more = ct + 1 < ct1;
     if (more) {
-      fetch_tile(W, ldw, (ct + 1) * RU, nt, 1, wr);
+#pragma unroll
+      for (int u = 0; u < 2; ++u) wr[u] = fetch_one(W, ldw, (ct + 1) * RU_N, nt, 1, t + 256 * u);
       load_c(ct + 1, cfn);
     }
-    const double* Wb = Ws + buf * RU * RU_LD;
-    double acc[4][2][2] = {};
+    const double* Wb = Ws + buf * RU_N * RU_LD;
+    double acc[2][2][2] = {};
 #pragma unroll
     for (int ks = 0; ks < QW / 4; ++ks) {
-      double a[4], b[2];
+      double a[2], b[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = Vs[(32 * wm + 8 * i + g) * RU_LD + 4 * ks + c];
+      for (int i = 0; i < 2; ++i) a[i] = Vs[(16 * wm + 8 * i + g) * RU_LD + 4 * ks + c];
 #pragma unroll
       for (int j = 0; j < 2; ++j) b[j] = Wb[(16 * wn + 8 * j + g) * RU_LD + 4 * ks + c];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int r = r0 + 32 * wm + 8 * i + g;
+    for (int i = 0; i < 2; ++i) {
+      const int r = r0 + 16 * wm + 8 * i + g;
       if (r >= rows) continue;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
-        const int col = ct * RU + 16 * wn + 8 * j + 2 * c;
+        const int col = ct * RU_N + 16 * wn + 8 * j + 2 * c;
         double* dst = C + static_cast<int64_t>(r) * ldc + col;
         const double2 o = make_double2(cf[i][j].x - acc[i][j][0], cf[i][j].y - acc[i][j][1]);
         if (vec && col + 1 < nt) *reinterpret_cast<double2*>(dst) = o;
@@ -889,9 +885,10 @@ __global__ void __launch_bounds__(256, 2) rank_update_kernel(double* __restrict_
       }
     }
     if (more) {
-      stage_tile(Ws + (buf ^ 1) * RU * RU_LD, wr);
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int u = 0; u < 2; ++u) stage_one(Ws + (buf ^ 1) * RU_N * RU_LD, t + 256 * u, wr[u]);
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) cf[i][j] = cfn[i][j];
     }
@@ -915,8 +912,8 @@ int launch_rank_update(double* C, int64_t ldc, const double* V, int64_t ldv, con
     NPW_CUDA_CHECK(cudaFuncSetAttribute(rank_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, RU_SMEM));
     g_ru_attr[dev] = true;
   }
-  const int64_t stripes = (rows + RU - 1) / RU, nct = (nt + RU - 1) / RU;
-  int64_t groups = (12 * 148 + stripes - 1) / stripes;      // enough CTAs for ~6 waves at 2 per SM
+  const int64_t stripes = (rows + RU - 1) / RU, nct = (nt + RU_N - 1) / RU_N;
+  int64_t groups = (24 * 148 + stripes - 1) / stripes;      // enough CTAs for ~8 waves at 3 per SM
   if (groups > nct) groups = nct;
   if (groups < 1) groups = 1;
   const int tiles_per_cta = static_cast<int>((nct + groups - 1) / groups);
