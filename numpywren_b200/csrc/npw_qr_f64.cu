@@ -362,6 +362,21 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
   auto gather = [&](int step, bool need_pivot, double& g_l, double& prow_l) {
     const uint64_t* base = p.packets + static_cast<size_t>(step & 1) * PK_STRIDE;
     const uint32_t seq = p.seq0 + static_cast<uint32_t>(step);
+    if (ngroups == 1) {
+      // a small grid (<= QGSZ CTAs, e.g. the 1024-row merges of a TSQR tree): everybody reads the members directly, one hop
+      const int m0 = warp, m1 = warp + RWARPS;
+      double v0, v1;
+      poll3(m0 < G ? base + static_cast<size_t>(m0) * PK_PER_VEC + 2 * lane : nullptr,
+            m1 < G ? base + static_cast<size_t>(m1) * PK_PER_VEC + 2 * lane : nullptr,
+            need_pivot ? base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane : nullptr, seq, v0, v1, prow_l);
+      s_red[warp][lane] = v0 + v1;
+      __syncthreads();
+      double t = 0.0;
+#pragma unroll
+      for (int q = 0; q < RWARPS; ++q) t += s_red[q][lane];
+      g_l = t;
+      return;
+    }
     if (leader) {                                           // CTA-uniform
       const int m0 = warp, m1 = warp + RWARPS;
       double v0, v1, v2;
@@ -786,7 +801,8 @@ constexpr int RU_SMEM = (RU + 2 * RU_N) * RU_LD * static_cast<int>(sizeof(double
 // ~80 registers, three CTAs per SM, each with the loads of two tiles outstanding.
 __global__ void __launch_bounds__(256, 3) rank_update_kernel(double* __restrict__ C, int64_t ldc, const double* __restrict__ V,
                                                              int64_t ldv, const double* __restrict__ W, int64_t ldw, int rows, int nt,
-                                                             int k, int vec, int vecv, int tiles_per_cta) {
+                                                             int k, int vec, int vecv, int tiles_per_cta,
+                                                             double* __restrict__ Rrows, int64_t ldr, int rrows) {
   extern __shared__ __align__(16) double ru_smem[];
   double* Vs = ru_smem;                                     // [RU][RU_LD]
   double* Ws = ru_smem + RU * RU_LD;                        // [2][RU_N][RU_LD]
@@ -882,6 +898,11 @@ __global__ void __launch_bounds__(256, 3) rank_update_kernel(double* __restrict_
           if (col < nt) dst[0] = o.x;
           if (col + 1 < nt) dst[1] = o.y;
         }
+        if (r < rrows) {                                   // the first `rrows` rows of the updated block are final rows of R
+          double* rd = Rrows + static_cast<int64_t>(r) * ldr + col;
+          if (col < nt) rd[0] = o.x;
+          if (col + 1 < nt) rd[1] = o.y;
+        }
       }
     }
     if (more) {
@@ -900,7 +921,7 @@ __global__ void __launch_bounds__(256, 3) rank_update_kernel(double* __restrict_
 bool g_ru_attr[64] = {};
 
 int launch_rank_update(double* C, int64_t ldc, const double* V, int64_t ldv, const double* W, int64_t ldw, int64_t rows,
-                       int64_t nt, int k, cudaStream_t st) {
+                       int64_t nt, int k, double* Rrows, int64_t ldr, int rrows, cudaStream_t st) {
   if (rows <= 0 || nt <= 0 || k <= 0) return NPW_OK;
   if (k > QW || !aligned16(W, ldw)) {
     set_error("rank update: k = %d > 32 or unaligned W", k);
@@ -919,7 +940,8 @@ int launch_rank_update(double* C, int64_t ldc, const double* V, int64_t ldv, con
   const int tiles_per_cta = static_cast<int>((nct + groups - 1) / groups);
   dim3 grid(static_cast<unsigned>(stripes), static_cast<unsigned>((nct + tiles_per_cta - 1) / tiles_per_cta));
   rank_update_kernel<<<grid, 256, RU_SMEM, st>>>(C, ldc, V, ldv, W, ldw, static_cast<int>(rows), static_cast<int>(nt), k,
-                                                 aligned16(C, ldc) ? 1 : 0, aligned16(V, ldv) ? 1 : 0, tiles_per_cta);
+                                                 aligned16(C, ldc) ? 1 : 0, aligned16(V, ldv) ? 1 : 0, tiles_per_cta, Rrows, ldr,
+                                                 Rrows ? rrows : 0);
   NPW_LAUNCH_CHECK();
   return NPW_OK;
 }
@@ -1146,10 +1168,8 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
       rc = launch_tn(tmp, QW, C, ldv, Vp, ldv, rows, nt, w, partials, 0, T + j0 * ldt + j0, ldt, st);
       if (rc) return rc;
       // C -= V_p tmp^T
-      rc = launch_rank_update(C, ldv, Vp, ldv, tmp, QW, rows, nt, w, st);
-      if (rc) return rc;
-      // rows j0 .. j0+w-1 of the trailing columns are final rows of R
-      rc = launch_copy2d(R + j0 * ldr + j0 + w, ldr, C, ldv, w, nt, 0, st);
+      // ... and rows j0 .. j0+w-1 of the updated trailing columns are final rows of R (written by the same kernel)
+      rc = launch_rank_update(C, ldv, Vp, ldv, tmp, QW, rows, nt, w, R + j0 * ldr + j0 + w, ldr, w, st);
       if (rc) return rc;
     }
   }
