@@ -41,6 +41,14 @@ constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * STAGES * 8;
 constexpr int RASTER_GROUP = 8;
 
 // tile-rows per raster group; NPW_B200_RASTER overrides the default (tuning knob, read once)
+inline int l2_hint_mode() {
+  static int v = [] {
+    const char* e = getenv("NPW_B200_L2HINT");
+    return e ? atoi(e) : 0;
+  }();
+  return v;
+}
+
 inline int raster_group() {
   static int v = [] {
     const char* e = getenv("NPW_B200_RASTER");
@@ -59,6 +67,7 @@ struct GemmArgs {
   int lower_only;
   int grid_m, grid_n;
   int raster;          // tile-rows per raster group
+  int l2hint;          // 1: A panel evict_last, C0 / C evict_first (the row panels of a raster group are what L2 should keep)
   int vec_ok;
 };
 
@@ -121,8 +130,13 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         mbar_wait(&empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         uint8_t* st = smem + s * STAGE_BYTES;
-        tma_load_2d(st, &tmA, &full[s], it * BK, tile_m * BM);
-        tma_load_2d(st + STAGE_A, &tmB, &full[s], it * BK, tile_n * BN);
+        if (p.l2hint) {
+          tma_load_2d_hint(st, &tmA, &full[s], it * BK, tile_m * BM, L2_EVICT_LAST);
+          tma_load_2d_hint(st + STAGE_A, &tmB, &full[s], it * BK, tile_n * BN, L2_EVICT_NORMAL);
+        } else {
+          tma_load_2d(st, &tmA, &full[s], it * BK, tile_m * BM);
+          tma_load_2d(st + STAGE_A, &tmB, &full[s], it * BK, tile_n * BN);
+        }
       }
     }
     return;
@@ -217,7 +231,8 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         for (int i = 0; i < 4; ++i)
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            sv[i][j] = *reinterpret_cast<const double2*>(p.C0 + static_cast<int64_t>(row0 + (ib + i) * 8) * p.ldc0 + col0 + j * 8);
+            sv[i][j] = p.l2hint ? ld_global_hint(p.C0 + static_cast<int64_t>(row0 + (ib + i) * 8) * p.ldc0 + col0 + j * 8, L2_EVICT_FIRST)
+                                : *reinterpret_cast<const double2*>(p.C0 + static_cast<int64_t>(row0 + (ib + i) * 8) * p.ldc0 + col0 + j * 8);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -231,7 +246,8 @@ gemm_nt_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             o.x = p.alpha * acc[ib + i][j][0];
             o.y = p.alpha * acc[ib + i][j][1];
           }
-          *reinterpret_cast<double2*>(p.C + static_cast<int64_t>(row0 + (ib + i) * 8) * p.ldc + col0 + j * 8) = o;
+          if (p.l2hint) st_global_hint(p.C + static_cast<int64_t>(row0 + (ib + i) * 8) * p.ldc + col0 + j * 8, o, L2_EVICT_FIRST);
+          else *reinterpret_cast<double2*>(p.C + static_cast<int64_t>(row0 + (ib + i) * 8) * p.ldc + col0 + j * 8) = o;
         }
     }
     return;
@@ -385,6 +401,7 @@ int launch_gemm(double* C, int64_t ldc, const double* C0, int64_t ldc0, const do
     p.grid_m = static_cast<int>((m + BM - 1) / BM);
     p.grid_n = static_cast<int>((n + BN - 1) / BN);
     p.raster = raster_group();
+    p.l2hint = l2_hint_mode();
     p.vec_ok = ((reinterpret_cast<uintptr_t>(C) & 15u) == 0) && (ldc % 2 == 0) &&
                (C0 == nullptr || (((reinterpret_cast<uintptr_t>(C0) & 15u) == 0) && (ldc0 % 2 == 0)));
     gemm_nt_tma_kernel<<<p.grid_m * p.grid_n, NTHREADS, SMEM_BYTES, stream>>>(tmA, tmB, p);
