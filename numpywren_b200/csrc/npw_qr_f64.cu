@@ -302,6 +302,7 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
   __shared__ double s_part[RWARPS][QW];
   __shared__ double s_red[RWARPS][QW];
   __shared__ double s_red2[RWARPS][QW];
+  __shared__ double s_prow[QW];
   __shared__ double s_T[QW][QW + 1];
   __shared__ double s_Z[QW][QW];
   __shared__ double s_tau[QW];
@@ -366,15 +367,18 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
       // a small grid (<= QGSZ CTAs, e.g. the 1024-row merges of a TSQR tree): everybody reads the members directly, one hop
       const int m0 = warp, m1 = warp + RWARPS;
       double v0, v1;
+      double pv;
       poll3(m0 < G ? base + static_cast<size_t>(m0) * PK_PER_VEC + 2 * lane : nullptr,
             m1 < G ? base + static_cast<size_t>(m1) * PK_PER_VEC + 2 * lane : nullptr,
-            need_pivot ? base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane : nullptr, seq, v0, v1, prow_l);
+            (need_pivot && warp == 0) ? base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane : nullptr, seq, v0, v1, pv);
       s_red[warp][lane] = v0 + v1;
+      if (warp == 0) s_prow[lane] = pv;
       __syncthreads();
       double t = 0.0;
 #pragma unroll
       for (int q = 0; q < RWARPS; ++q) t += s_red[q][lane];
       g_l = t;
+      prow_l = s_prow[lane];
       return;
     }
     if (leader) {                                           // CTA-uniform
@@ -392,16 +396,20 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
       }
     }
     const int g0 = warp, g1 = warp + RWARPS;
-    double v0, v1;
+    // the pivot row is polled by ONE warp per CTA and handed on through shared memory: with all 8 warps of all 148 CTAs
+    // polling the same 512 bytes, the reads queued at one L2 slice in front of the very store they were waiting for
+    double v0, v1, pv;
     poll3(g0 < ngroups ? base + static_cast<size_t>(PK_GROUP0 + g0) * PK_PER_VEC + 2 * lane : nullptr,
           g1 < ngroups ? base + static_cast<size_t>(PK_GROUP0 + g1) * PK_PER_VEC + 2 * lane : nullptr,
-          need_pivot ? base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane : nullptr, seq, v0, v1, prow_l);
+          (need_pivot && warp == RWARPS - 1) ? base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane : nullptr, seq, v0, v1, pv);
     s_red[warp][lane] = v0 + v1;
+    if (warp == RWARPS - 1) s_prow[lane] = pv;
     __syncthreads();
     double t = 0.0;
 #pragma unroll
     for (int q = 0; q < RWARPS; ++q) t += s_red[q][lane];
     g_l = t;
+    prow_l = s_prow[lane];
   };
   auto block_sum_and_publish = [&](int step, double acc) {
     s_part[warp][lane] = acc;
