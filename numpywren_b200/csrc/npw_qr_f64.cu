@@ -60,6 +60,7 @@ struct PanelArgs {
   uint64_t* packets;   // PK_BYTES, zeroed once per factorisation
   uint32_t seq0;       // first sequence number of this launch (unique within the factorisation, never 0)
   int* err;            // set to 1 if a poll timed out
+  long long* prof;     // NPW_QR_PROFILE builds only: [cta][8] accumulated cycles per phase of a column step
 };
 
 // A double as two self-validating 64-bit packets (each 8-byte access is single-copy atomic, so no fence or separate
@@ -360,9 +361,17 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
     v1 = s1 ? ll_value(b0, b1) : 0.0;
     v2 = s2 ? ll_value(c0, c1) : 0.0;
   };
+#ifdef NPW_QR_PROFILE
+  long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long pt = clock64();
+#define QR_STAMP(i) do { const long long _n = clock64(); pf[i] += _n - pt; pt = _n; } while (0)
+#else
+#define QR_STAMP(i) do { } while (0)
+#endif
   auto gather = [&](int step, bool need_pivot, double& g_l, double& prow_l) {
     const uint64_t* base = p.packets + static_cast<size_t>(step & 1) * PK_STRIDE;
     const uint32_t seq = p.seq0 + static_cast<uint32_t>(step);
+    QR_STAMP(7);                                            // whatever happened since the last stamp (publish etc.)
     if (ngroups == 1) {
       // a small grid (<= QGSZ CTAs, e.g. the 1024-row merges of a TSQR tree): everybody reads the members directly, one hop
       const int m0 = warp, m1 = warp + RWARPS;
@@ -395,6 +404,7 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
         ll_store(const_cast<uint64_t*>(base) + static_cast<size_t>(PK_GROUP0 + grp_id) * PK_PER_VEC + 2 * lane, t, seq);
       }
     }
+    QR_STAMP(0);                                            // leader stage (0 for the others)
     const int g0 = warp, g1 = warp + RWARPS;
     // the pivot row is polled by ONE warp per CTA and handed on through shared memory: with all 8 warps of all 148 CTAs
     // polling the same 512 bytes, the reads queued at one L2 slice in front of the very store they were waiting for
@@ -402,6 +412,7 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
     poll3(g0 < ngroups ? base + static_cast<size_t>(PK_GROUP0 + g0) * PK_PER_VEC + 2 * lane : nullptr,
           g1 < ngroups ? base + static_cast<size_t>(PK_GROUP0 + g1) * PK_PER_VEC + 2 * lane : nullptr,
           (need_pivot && warp == RWARPS - 1) ? base + static_cast<size_t>(MAX_GRID) * PK_PER_VEC + 2 * lane : nullptr, seq, v0, v1, pv);
+    QR_STAMP(1);                                            // poll of the group sums
     s_red[warp][lane] = v0 + v1;
     if (warp == RWARPS - 1) s_prow[lane] = pv;
     __syncthreads();
@@ -410,6 +421,7 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
     for (int q = 0; q < RWARPS; ++q) t += s_red[q][lane];
     g_l = t;
     prow_l = s_prow[lane];
+    QR_STAMP(2);                                            // barrier + sum
   };
   auto block_sum_and_publish = [&](int step, double acc) {
     s_part[warp][lane] = acc;
@@ -452,6 +464,7 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
     if (threadIdx.x == 0) s_tau[j] = tau;
     const double wc = (lane > j && lane_ok) ? prow_l + scale * g_l : 0.0;
     const double tw = tau * wc;
+    QR_STAMP(3);                                            // Householder scalars
     const bool right = lane > j, diag = lane == j, left = lane < j;
     const bool next = j + 1 < w;
     // per-lane constants that turn the column roles into arithmetic: new = v * kv + v_j[r] * cv
@@ -503,9 +516,15 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
         for (int i = 0; i < RPIV; ++i) v[i] = (i == ip && !left) ? nv : v[i];
       }
     }
+    QR_STAMP(4);                                            // pass over the rows
     if (next) publish_row(j + 1, gj + 1);
     block_sum_and_publish(j + 1, (a4[0] + a4[1]) + (a4[2] + a4[3]));
+    QR_STAMP(5);                                            // block sum + publish
   }
+#ifdef NPW_QR_PROFILE
+  if (p.prof != nullptr && (threadIdx.x == 0 || threadIdx.x == RTHREADS - 1))
+    for (int i = 0; i < 8; ++i) atomicAdd(reinterpret_cast<unsigned long long*>(p.prof) + (cta * 2 + (threadIdx.x ? 1 : 0)) * 8 + i, static_cast<unsigned long long>(pf[i]));
+#endif
   {
     double g_l, prow_l;
     gather(w, false, g_l, prow_l);
@@ -1052,7 +1071,7 @@ struct QrWork {
 QrWork qr_work_layout(int64_t m, int64_t n) {
   QrWork w;
   size_t off = 0;
-  w.scratch = off; off += align256(PK_BYTES + 256);                                   // packets + error word
+  w.scratch = off; off += align256(PK_BYTES + 256 + MAX_GRID * 2 * 8 * sizeof(long long));   // packets + error word + (profile builds) phase counters
   w.tau = off; off += align256(static_cast<size_t>(n) * sizeof(double));
   w.tmp = off; off += align256(static_cast<size_t>(n) * QW * sizeof(double));        // Wt T_p
   w.gram = off; off += align256(static_cast<size_t>(n) * n * sizeof(double));        // G = V^T V
@@ -1136,7 +1155,7 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
   int rc;
   // the all-gather packets validate themselves by sequence number: start every factorisation from zeroed packets
   // (sequence numbers are unique within a factorisation and never 0)
-  NPW_CUDA_CHECK(cudaMemsetAsync(packets, 0, PK_BYTES + 256, st));
+  NPW_CUDA_CHECK(cudaMemsetAsync(packets, 0, PK_BYTES + 256 + MAX_GRID * 2 * 8 * sizeof(long long), st));
   if (V != A) {
     rc = launch_copy2d(V, ldv, A, lda, m, n, 0, st);
     if (rc) return rc;
@@ -1153,6 +1172,7 @@ int npw_geqrt_f64(double* V, int64_t ldv, double* T, int64_t ldt, double* R, int
     PanelArgs pa;
     pa.V = V; pa.ldv = ldv; pa.m = static_cast<int>(m); pa.j0 = static_cast<int>(j0); pa.w = w;
     pa.R = R; pa.ldr = ldr; pa.T = T; pa.ldt = ldt; pa.tau = tau; pa.packets = packets; pa.seq0 = seq; pa.err = err;
+    pa.prof = reinterpret_cast<long long*>(wb + wl.scratch + PK_BYTES + 256);
     seq += QW + 2;                                          // steps 0 .. w of this launch
     int g = static_cast<int>((rows + 127) / 128);           // >= 128 panel rows per CTA
     if (g > max_grid) g = max_grid;
