@@ -19,6 +19,8 @@
 //             T[0:j0, panel] = -T[0:j0,0:j0] G[0:j0,panel] T_pp  (one small kernel per panel).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "npw_common.cuh"
 
 namespace npw {
@@ -281,6 +283,7 @@ __global__ void __launch_bounds__(QTHREADS, 1) qr_panel_kernel(PanelArgs p) {
 // partial sums as the shared-memory variant up to the 4-way split of the accumulator; same all-gather protocol.
 // ------------------------------------------------------------------------------------------------
 constexpr int RTHREADS = 256, RWARPS = 8, RPW = 56;
+constexpr int RFEW = 16;                 // short row loops for CTAs with at most RFEW x RWARPS = 128 rows
 constexpr int RPIV = QW / RWARPS + 1;   // register rows of a warp that can be (or sit directly below) a pivot row of the launch
 
 // 224 registers x 256 threads leave 8192 of the SM's 65536 registers free ON PURPOSE: the kernel spins on packets from its
@@ -475,10 +478,12 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
     double a4[4] = {0.0, 0.0, 0.0, 0.0};
     // Each row adds, per lane: lane < j: V[r][i] v_j[r] (Gram); lane > j: x'_r P'[r][c] (dot products of column j+1, rows
     // below the next pivot).  Lane j itself collects a product nobody reads (the gathers use lanes != j only).
-    if (r_lo > p.j0 + w) {
-      // no pivot row in this CTA during this launch: every row is below the pivots (padding rows are all zero)
+    // The row loops exist in two unrolled lengths: all RPW register rows, or the first RFEW when the CTA holds at most
+    // RFEW x RWARPS rows (the 1024-row merges of a TSQR tree have 128 rows per CTA: 16 of the 56 register rows are real).
+    auto rows_all = [&](auto NRC) {
+      constexpr int NR = decltype(NRC)::value;
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) {
+      for (int i = 0; i < NR; ++i) {
         const double x = __shfl_sync(0xffffffffu, v[i], j);
         const double vr = x * scale;                  // v_j[r]
         const double nv = fma(vr, cv, v[i] * kv);
@@ -486,12 +491,11 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
         const double xn = __shfl_sync(0xffffffffu, nv, (j + 1) & 31);
         a4[i & 3] = fma(nv, left ? vr : xn, a4[i & 3]);
       }
-    } else {
-      // This CTA holds pivot rows of this launch.  They are among its first 32 rows (r_lo >= j0), i.e. register rows
-      // i < RPIV of some warp: only those need the predicates; rows at or above the pivot get v_j[r] = 0 (nothing
-      // changes; column j of a finished row is already 0).
+    };
+    auto rows_piv = [&](auto NRC) {
+      constexpr int NR = decltype(NRC)::value;
 #pragma unroll
-      for (int i = 0; i < RPW; ++i) {
+      for (int i = 0; i < NR; ++i) {
         const int r = r_lo + warp + RWARPS * i;
         const double x = __shfl_sync(0xffffffffu, v[i], j);
         const double vr = (i >= RPIV || r > gj) ? x * scale : 0.0;
@@ -500,6 +504,20 @@ __global__ void __maxnreg__(224) qr_panel_reg_kernel(PanelArgs p) {
         const double xn = __shfl_sync(0xffffffffu, nv, (j + 1) & 31);
         a4[i & 3] = fma(nv, left ? vr : ((i >= RPIV || r > gj + 1) ? xn : 0.0), a4[i & 3]);
       }
+    };
+    using NFull = std::integral_constant<int, RPW>;
+    using NFew = std::integral_constant<int, RFEW>;
+    const bool few = per <= RFEW * RWARPS;
+    if (r_lo > p.j0 + w) {
+      // no pivot row in this CTA during this launch: every row is below the pivots (padding rows are all zero)
+      if (few) rows_all(NFew{});
+      else rows_all(NFull{});
+    } else {
+      // This CTA holds pivot rows of this launch.  They are among its first 32 rows (r_lo >= j0), i.e. register rows
+      // i < RPIV of some warp: only those need the predicates; rows at or above the pivot get v_j[r] = 0 (nothing
+      // changes; column j of a finished row is already 0).
+      if (few) rows_piv(NFew{});
+      else rows_piv(NFull{});
       // ---- pivot row (one warp of one CTA): R(gj, c) = P[gj][c] - tau w_c, diagonal beta; the row of V becomes e_j
       // (the loop above left its lanes != j untouched)
       if (gj >= r_lo && gj < r_hi && ((gj - r_lo) & (RWARPS - 1)) == warp) {
