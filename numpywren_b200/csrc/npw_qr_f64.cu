@@ -4,14 +4,17 @@
 //
 // Blocked right-looking algorithm, panel width 32:
 //   panel   : ONE kernel (co-resident grid, <= 1 CTA per SM) factors the (m-j0) x 32 panel.  Rows are split over the
-//             CTAs; each CTA keeps its row chunk in shared memory for all 32 column steps.  Per column there is a single
-//             pass over the rows that (i) applies reflector j, (ii) accumulates the dot products column j+1 needs
-//             (norm + w = P^T x) and (iii) the Gram entries V[:,0:j]^T v_j that dlarft needs, all in one 32-lane
-//             vector, followed by ONE all-gather of the per-CTA vectors.  The all-gather is flag-in-data: every double
-//             travels as two 64-bit packets {32 payload bits | 32-bit sequence number}; readers poll the packets
-//             themselves, so a column step costs one L2 store->load latency instead of a grid barrier plus a reduction
-//             (round 1: 14 us per column, cooperative grid.sync; now one hop).  Every CTA adds the vectors in the same
-//             fixed order, so all CTAs derive bit-identical Householder scalars and the result is deterministic.
+//             CTAs; each CTA keeps its rows in REGISTERS (qr_panel_reg_kernel: 8 warps x 56 rows x 32 lanes, up to 448
+//             rows per CTA; tiles with more rows per CTA use the shared-memory / global variants qr_panel_kernel) for all
+//             32 column steps.  Per column there is a single pass over the rows that (i) applies reflector j, (ii)
+//             accumulates the dot products column j+1 needs (norm + w = P^T x) and (iii) the Gram entries
+//             V[:,0:j]^T v_j that dlarft needs, all in one 32-lane vector, followed by ONE all-gather of the per-CTA
+//             vectors.  The all-gather is flag-in-data: every double travels as two 64-bit packets {32 payload bits |
+//             32-bit sequence number}; readers poll the packets themselves, so a column step costs L2 store->load
+//             latencies (two levels: groups of 12 CTAs, then the group sums; one level for <= 12 CTAs) instead of a grid
+//             barrier plus a reduction (round 1: 14-25 us per column with cooperative grid.sync; now 4.4 us).  Every
+//             CTA adds the vectors in the same fixed order, so all CTAs derive bit-identical Householder scalars and
+//             the result is deterministic.  Protocol model check: tests/test_qr_gather_protocol.py.
 //   update  : Wt = C^T V_p  split-K "TN" product on the fp64 tensor pipe (DMMA, k = rows), reduced in a fixed order
 //             and multiplied by T_p in the same kernel;  C -= V_p (Wt T_p)^T  by a streaming rank-32 DMMA kernel
 //             (HBM-bound: 2 x 32 flop per element read and written).
@@ -25,9 +28,6 @@
 
 namespace npw {
 
-int launch_gemm(double* C, int64_t ldc, const double* C0, int64_t ldc0, const double* A, int64_t lda, int transA,
-                const double* B, int64_t ldb, int transB, int64_t m, int64_t n, int64_t k, double alpha,
-                double beta, int lower_only, cudaStream_t stream);
 int launch_copy2d(double* dst, int64_t ldd, const double* src, int64_t lds, int64_t rows, int64_t cols, int trans,
                   cudaStream_t st);
 int launch_fill2d(double* A, int64_t lda, int64_t rows, int64_t cols, int mode, double value, cudaStream_t st);
