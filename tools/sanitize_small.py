@@ -31,10 +31,18 @@ for n in (8, 100, 128, 200, 384):
     assert np.allclose(X.cpu().numpy() @ np.linalg.cholesky(a).T, b)
     X2 = kernels.trsm(L, t(b))
     assert np.allclose(X2.cpu().numpy(), X.cpu().numpy())
-for (m, n) in [(64, 32), (300, 70), (1024, 64)]:
+# incl. a 16-CTA panel grid (two-level gather with two groups), several panels (TN product, rank update, T blocks) and an
+# unaligned leading dimension (generic TN kernel, scalar rank-update path)
+for (m, n) in [(64, 32), (300, 70), (1024, 64), (2048, 96), (600, 160), (130, 33)]:
     a = rs.randn(m, n)
     V, T, R = kernels.qr_factor(t(a))
     assert np.allclose(np.abs(R.cpu().numpy()), np.abs(np.linalg.qr(a)[1]))
+# fp64 syrk emulated on the int8 tensor cores (tcgen05 / TMEM / TMA 3-D)
+x, y, sm = rs.randn(256, 512), rs.randn(192, 512), rs.randn(256, 192)
+xd, xe = kernels.split_i8(t(x), 7)
+yd, ye = kernels.split_i8(t(y), 7)
+c = kernels.syrk_i8emu(t(sm), xd, xe, yd, ye).cpu().numpy()
+assert np.linalg.norm(c - (sm - x @ y.T)) / np.linalg.norm(sm - x @ y.T) < 1e-11
 p = [t(rs.randn(50, 30)) for _ in range(4)]
 kernels.add_matrices(*p); kernels.mul(p[0], p[1]); kernels.transpose(p[0])
 torch.cuda.synchronize()
