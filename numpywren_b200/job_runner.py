@@ -134,7 +134,7 @@ class TileEngine:
                            if n in self.compiled.scope}
         self._reads_left: Dict[Any, int] = {}
         self.freed_tiles = 0
-        # EXPERIMENTAL, off by default (NPW_B200_SYRK=i8emu): syrk products on the int8 tensor cores.
+        # optional, off by default (NPW_B200_SYRK=i8emu): syrk products on the int8 tensor cores.
         # The int8 digits of a panel tile are a per-tile by-product like invdiag: extracted once, reused by every syrk
         # of the tile's block row / column, dropped after the last one.
         self.syrk_mode = os.environ.get("NPW_B200_SYRK", "native")

@@ -436,9 +436,9 @@ def _gemm_any(out, c0, A, B, trans_a, trans_b, alpha, beta):
     return _gemm_into(out, c0, A, B, trans_a, trans_b, alpha, beta)
 
 
-# ----------------------------------------------------------------------------- EXPERIMENTAL: int8-tensor-core emulation
+# ----------------------------------------------------------------------------- optional: int8-tensor-core emulation
 def split_i8(x, digits=6):
-    """EXPERIMENTAL (never run on hardware in round 1).  fp64 tile -> (int8 digit planes [digits, rows, k],
+    """Optional path (off by default, tests/test_i8emu_gpu.py).  fp64 tile -> (int8 digit planes [digits, rows, k],
     int32 row exponents) for ``syrk_i8emu``: x = diag(2^e) sum_p 2^-(6+7p) x_p."""
     x = _rowmajor(x, "x")
     rows, k = x.shape
@@ -451,7 +451,7 @@ def split_i8(x, digits=6):
 
 
 def syrk_i8emu(s, xd, xe, yd, ye, out=None, lower=False):
-    """EXPERIMENTAL.  s - x.dot(y.T) from the int8 digits of x and y (``split_i8``): the product runs on the int8 tensor
+    """Optional path.  s - x.dot(y.T) from the int8 digits of x and y (``split_i8``): the product runs on the int8 tensor
     cores (tcgen05.mma kind::i8) with exact int32 group sums, the combination in fp64."""
     _check_tile(s, "s")
     sm = _rowmajor(s, "s")
