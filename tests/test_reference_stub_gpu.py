@@ -1,4 +1,4 @@
-"""The kernel-seam drop-in of INTEGRATION.md §2 (tools/reference_side_stub/kernels_b200.py): syrk / trsm / chol bound to the
+"""The kernel-seam drop-in of INTEGRATION.md §2 (tools/reference_side_stub/kernels_b200.py): syrk / trsm / chol / qr_factor bound to the
 C-ABI with ctypes + the CUDA runtime — NumPy in and out, no torch, nothing imported from numpywren_b200 — driven by the
 program logic of algs.CHOLESKY (the oracle's replay, with its three kernels replaced by the stub's) on the fixture written by
 the unmodified reference."""
@@ -47,3 +47,21 @@ def test_stub_chol_reports_non_spd_like_numpy(stub):
     x = np.random.RandomState(0).randn(96, 40)
     spd = x @ x.T + 96 * np.eye(96)
     assert np.allclose(stub.chol(spd), np.linalg.cholesky(spd), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["tsqr_256_32", "tsqr_128_16"])
+def test_tsqr_program_logic_over_the_stub_matches_the_reference_run(golden_dir, stub, monkeypatch, name):
+    g = np.load(os.path.join(golden_dir, name + ".npz"))
+    m, b, nlev = int(g["m"]), int(g["b"]), int(g["nlev"])
+    A = orc.OracleBigMatrix("X_stub", (m, b), (b, b))
+    orc.shard_matrix(A, g["X"])
+    monkeypatch.setattr(orc, "qr_factor", stub.qr_factor)
+    Rs, Vs, Ts = orc.run_tsqr(A)
+    R = Rs.get_block(nlev, 0)
+    assert np.linalg.norm(R - g["R"]) / np.linalg.norm(g["R"]) < 1e-10
+    for k in g.files:
+        if k[:2] in ("R_", "V_") or k.startswith("Tq_"):
+            lvl, j = (int(x) for x in k.split("_")[1:])
+            mat = {"R": Rs, "V": Vs, "Tq": Ts}[k.split("_")[0]]
+            got = mat.get_block(lvl, j)
+            assert np.linalg.norm(got - g[k]) / max(np.linalg.norm(g[k]), 1e-300) < 1e-10, k

@@ -24,6 +24,9 @@ _lib.npw_potrf_l_f64.argtypes = [_vp, _i64, _vp, _i64, _i64, _vp, _vp, _vp, _vp]
 _lib.npw_trsm_work_bytes.restype = _lib.npw_potrf_work_bytes.restype = ctypes.c_size_t
 _lib.npw_trsm_work_bytes.argtypes = [_i64, _i64]
 _lib.npw_potrf_work_bytes.argtypes = [_i64]
+_lib.npw_geqrt_f64.argtypes = [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i64, _vp, _vp]
+_lib.npw_geqrt_work_bytes.restype = ctypes.c_size_t
+_lib.npw_geqrt_work_bytes.argtypes = [_i64, _i64]
 _H2D, _D2H = cudart.cudaMemcpyKind.cudaMemcpyHostToDevice, cudart.cudaMemcpyKind.cudaMemcpyDeviceToHost
 
 
@@ -87,3 +90,17 @@ def chol(x, *args, **kwargs):                # kernels.chol (kernels.py:225-226)
         cudart.cudaFree(pa)
         raise np.linalg.LinAlgError("Matrix is not positive definite")
     return _to_host(pa, (n, n))
+
+
+def qr_factor(*blocks, **kwargs):            # kernels.qr_factor (kernels.py:127-130): fast_qr(np.vstack(blocks)) -> (V, T, R)
+    a = np.vstack(blocks)
+    m, n = a.shape
+    assert m >= n, "the wide form (slow_qr) is sequenced by numpywren_b200/qr.py from the same entry points"
+    pv, _ = _to_dev(a)
+    pt, pr = _malloc(n * n * 8), _malloc(n * n * 8)
+    w = _malloc(_lib.npw_geqrt_work_bytes(m, n))
+    rc = _lib.npw_geqrt_f64(pv, n, pt, n, pr, n, pv, n, m, n, w, None)
+    assert rc == 0, rc
+    V, T, R = _to_host(pv, (m, n)), _to_host(pt, (n, n)), _to_host(pr, (n, n))
+    cudart.cudaFree(w)
+    return V, T, R
