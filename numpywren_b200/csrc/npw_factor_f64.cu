@@ -9,7 +9,8 @@
 //   solve_phase  a chunk of rows is solved against that block by block forward substitution (X = P L_jj^{-T}, in place);
 //   inverse_phase (only for npw_trtri_diag_f64 / the optional invdiag output) L_jj^{-1} by block substitution.
 //
-//   potrf (two-level right-looking):                      trsm (recursive on the columns of X, in place):
+//   potrf (two-level right-looking):                      trsm (recursive on the columns of X, in place; optionally two
+//                                                         row halves on two streams, NPW_B200_TRSM_SPLIT=1):
 //     for each 512-column block column                      X1 = trsm(B1, L11)
 //       for each 128-column panel j (ONE launch):           B2 -= X1 * L21^T        (GEMM, large k)
 //         every CTA factors A_jj redundantly, then          X2 = trsm(B2, L22)
@@ -591,7 +592,11 @@ int npw_trsm_rlt_f64(double* B_out, int64_t ldbo, const double* L, int64_t ldl, 
     if (rc) return rc;
   }
   // two row halves on two streams when both halves still fill the GPU's GEMM grid (see ForkJoin)
-  static const bool split_ok = [] { const char* e = getenv("NPW_B200_TRSM_SPLIT"); return !e || atoi(e) != 0; }();
+  // OPT-IN (NPW_B200_TRSM_SPLIT=1): measured 3.64 -> 3.49 ms per 4096^2 solve and +0.1 % on the one-GPU Cholesky, but the
+  // extra side streams were never run inside the 8-GPU engine, whose exchange parks wait_signal kernels on per-peer
+  // streams and relies on every stream having its own hardware queue (CUDA_DEVICE_MAX_CONNECTIONS=32): not worth a
+  // possible false dependency there.
+  static const bool split_ok = [] { const char* e = getenv("NPW_B200_TRSM_SPLIT"); return e && atoi(e) != 0; }();
   if (split_ok && m >= 2048 && n >= 1024) {
     if (npw::ForkJoin* fj = npw::acquire_fork_join(st)) {
       const int64_t h = ((m / 2 + npw::NB - 1) / npw::NB) * npw::NB;
